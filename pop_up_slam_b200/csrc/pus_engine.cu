@@ -1,0 +1,927 @@
+// pus_engine.cu -- persistent LM kernel entry, host-side engine (HBM layout, upload / solve /
+// download) and the extern "C" entry points declared in include/popup_gpu.h.
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC ...
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/popup_gpu.h"
+#include "pus_kernels.cuh"
+
+namespace pus {
+
+// ---------------------------------------------------------------------------------------------
+// device: LM / GN driver
+// ---------------------------------------------------------------------------------------------
+struct Timer {
+  bool on;
+  unsigned long long t0;
+  LmResult* res;
+  __device__ Timer(bool o, LmResult* r) : on(o), t0(0), res(r) { if (on) t0 = gtime(); }
+  __device__ void lap(int slot) {
+    if (on) {
+      unsigned long long t = gtime();
+      res->phase_ns[slot] += t - t0;
+      t0 = t;
+    }
+  }
+};
+
+__device__ void linearize(Phase& ph, Ctx& c) {
+  ph.lin_pose_plane();
+  ph.lin_other();
+  team_barrier(c);
+  ph.assemble();
+  team_barrier(c);
+}
+
+// Schur complement set-up for a damping value; returns the buffer index of A_c^-1
+__device__ int schur_setup(Phase& ph, Ctx& c, double lambda) {
+  ph.plane_inverse(lambda);
+  team_barrier(c);
+  ph.build_blocks(lambda);
+  ph.coarse_wc();
+  team_barrier(c);
+  ph.coarse_assemble(lambda);
+  team_barrier(c);
+  return ph.coarse_invert();
+}
+
+// Solve (Hpp_d - W Hll_d^-1 W^T) x = -gp + W Hll_d^-1 gl by preconditioned CG, then back-substitute the
+// planes.  Returns |delta|; *its = PCG iterations.
+__device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambda, int acinv, int* its) {
+  ph.sweep_poses();  // with vl = Hll^-1 gl (plane_inverse)
+  team_barrier(c);
+  ph.make_rhs();
+  team_barrier(c);
+  double v[2];
+  int rcb = 0, cur = 0, it = 0;
+  v[0] = ph.precondition(0.0, nullptr, acinv, G.rcpart[0], G.rcpart[1], true);
+  team_reduce<1>(c, G.red, v);
+  rcb = 1;
+  const double rz0 = v[0];
+  double rz = rz0, beta = 0.0;
+  const double tol2 = G.prm.pcg_tol * G.prm.pcg_tol;
+  if (rz0 > 0.0) {
+    while (it < G.prm.pcg_max_iter) {
+      ph.update_direction(cur, beta);
+      ph.sweep_planes(G.z, G.pv[cur], beta);
+      team_barrier(c);
+      ph.solve_planes(0);
+      team_barrier(c);
+      ph.sweep_poses();
+      team_barrier(c);
+      v[0] = ph.apply_pose_side(G.pv[cur ^ 1], lambda, G.q, G.qcpart);
+      team_reduce<1>(c, G.red, v);
+      const double pq = v[0];
+      if (!(pq > 0.0)) break;  // breakdown (not SPD / exhausted precision)
+      const double alpha = rz / pq;
+      v[0] = ph.precondition(alpha, G.pv[cur ^ 1], acinv, G.rcpart[rcb], G.rcpart[rcb ^ 1], false);
+      team_reduce<1>(c, G.red, v);
+      rcb ^= 1;
+      it++;
+      const double rz_new = v[0];
+      if (!(rz_new > tol2 * rz0)) break;
+      beta = rz_new / rz;
+      rz = rz_new;
+      cur ^= 1;
+    }
+  }
+  *its = it;
+  // planes: dl = Hll_d^-1 (-gl - W^T x)
+  ph.sweep_planes(G.x, nullptr, 0.0);
+  team_barrier(c);
+  v[0] = ph.solve_planes(1) + ph.norm_x();
+  team_reduce<1>(c, G.red, v);
+  return sqrt(v[0]);
+}
+
+__device__ void run_graph(const DevGraph& G, Ctx& c) {
+  Phase ph(G, c);
+  const LmParams& P = G.prm;
+  const bool lead = (c.rank == 0 && threadIdx.x == 0);
+  LmResult* res = G.res;
+  Timer tm(lead, res);
+  if (lead) {
+    res->iterations = 0; res->accepted = 0; res->relin = 0; res->chi2_evals = 0; res->pcg_iters = 0;
+    res->trace_n = 0; res->status = 0; res->chi2_initial = 0; res->chi2_final = 0;
+    for (int i = 0; i < 8; i++) res->phase_ns[i] = 0;
+  }
+  if (P.restore_init) { ph.restore_init(); team_barrier(c); }
+  if (P.mode == MODE_CHI2) {
+    double e = ph.chi2(false);
+    if (lead) { res->chi2_final = e; res->chi2_initial = e; res->chi2_evals = 1; }
+    return;
+  }
+  if (P.mode == MODE_DEBUG) {
+    if (P.debug_stage == 3) {  // q = S * pv[0] with the current linearisation / Schur set-up
+      ph.sweep_planes(G.pv[0], nullptr, 0.0);
+      team_barrier(c);
+      ph.solve_planes(0);
+      team_barrier(c);
+      ph.sweep_poses();
+      team_barrier(c);
+      ph.apply_pose_side(G.pv[0], P.debug_lambda, G.q, nullptr);
+      team_barrier(c);
+      return;
+    }
+    linearize(ph, c);
+    if (lead) res->relin = 1;
+    if (P.debug_stage >= 1) {
+      int acinv = schur_setup(ph, c, P.debug_lambda);
+      if (lead) res->status = acinv;
+      if (P.debug_stage >= 2) {
+        int its = 0;
+        double dn = schur_solve(ph, c, G, P.debug_lambda, acinv, &its);
+        if (lead) { res->pcg_iters = its; res->chi2_final = dn; }
+      }
+    }
+    return;
+  }
+
+  // ---- Optimizer::levenberg_marquardt / gauss_newton / relinearize ----
+  tm.lap(7);
+  linearize(ph, c);
+  tm.lap(0);
+  int relin = 1, nchi = 0, accepted = 0, iter = 0, its = 0;
+  long long pcg_total = 0;
+  double lambda = (P.method == 1 && P.mode == MODE_BATCH) ? P.lambda0 : 0.0;
+  double err = 0.0;
+  if (P.mode == MODE_BATCH) { err = ph.chi2(false); nchi++; }
+  tm.lap(4);
+  const double err0 = err;
+  int acinv = schur_setup(ph, c, lambda);
+  tm.lap(1);
+  double dnorm = schur_solve(ph, c, G, lambda, acinv, &its);
+  pcg_total += its;
+  tm.lap(2);
+  if (P.mode == MODE_UPDATE) {
+    // Optimizer::relinearize (GN branch): estimate = linpoint (+) h_gn
+    ph.apply_delta();
+    team_barrier(c);
+    ph.accept_trial();
+    team_barrier(c);
+    tm.lap(3);
+  } else if (P.method == 1) {
+    int last_pcg = its;
+    while ((P.max_iter <= 0 || iter < P.max_iter) && dnorm > P.eps2 && err > P.eps_abs) {
+      iter++;
+      ph.apply_delta();
+      team_barrier(c);
+      tm.lap(3);
+      double err_new = ph.chi2(true);
+      nchi++;
+      tm.lap(4);
+      double diff = err - err_new;
+      bool stop = false;
+      if (lead && iter <= kTraceCap) {
+        LmTrace* t = G.trace;
+        t->lambda[iter - 1] = lambda; t->chi2_new[iter - 1] = err_new; t->chi2_before[iter - 1] = err;
+        t->delta_norm[iter - 1] = dnorm; t->accepted[iter - 1] = diff > 0.0 ? 1 : 0; t->pcg[iter - 1] = last_pcg;
+      }
+      if (diff > 0.0) {
+        accepted++;
+        ph.accept_trial();
+        team_barrier(c);
+        if (diff < P.eps_rel * err) {
+          err = err_new;  // the linearisation point keeps the step (Optimizer.cpp:431-435, 466)
+          stop = true;
+        } else {
+          lambda /= P.lambda_factor;
+          err = err_new;
+          tm.lap(3);
+          linearize(ph, c);
+          relin++;
+          tm.lap(0);
+        }
+      } else {
+        lambda *= P.lambda_factor;
+      }
+      if (stop) break;
+      acinv = schur_setup(ph, c, lambda);
+      tm.lap(1);
+      dnorm = schur_solve(ph, c, G, lambda, acinv, &its);
+      last_pcg = its;
+      pcg_total += its;
+      tm.lap(2);
+    }
+  } else {
+    double diff = P.eps_rel * err + 1;
+    int last_pcg = its;
+    while ((P.max_iter <= 0 || iter < P.max_iter) && dnorm > P.eps2 && err > P.eps_abs && fabs(diff) > P.eps_rel * err) {
+      iter++;
+      ph.apply_delta();
+      team_barrier(c);
+      ph.accept_trial();
+      team_barrier(c);
+      tm.lap(3);
+      linearize(ph, c);
+      relin++;
+      tm.lap(0);
+      double err_new = ph.chi2(false);
+      nchi++;
+      tm.lap(4);
+      diff = err - err_new;
+      if (lead && iter <= kTraceCap) {
+        LmTrace* t = G.trace;
+        t->lambda[iter - 1] = 0.0; t->chi2_new[iter - 1] = err_new; t->chi2_before[iter - 1] = err;
+        t->delta_norm[iter - 1] = dnorm; t->accepted[iter - 1] = 1; t->pcg[iter - 1] = last_pcg;
+      }
+      accepted++;
+      err = err_new;
+      acinv = schur_setup(ph, c, 0.0);
+      tm.lap(1);
+      dnorm = schur_solve(ph, c, G, 0.0, acinv, &its);
+      last_pcg = its;
+      pcg_total += its;
+      tm.lap(2);
+    }
+  }
+  if (lead) {
+    res->iterations = iter; res->accepted = accepted; res->relin = relin; res->chi2_evals = nchi;
+    res->pcg_iters = pcg_total; res->chi2_initial = err0; res->chi2_final = err;
+    res->trace_n = iter < kTraceCap ? iter : kTraceCap;
+  }
+}
+
+__global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs, int n_graphs, int team_ctas, unsigned* bars) {
+  extern __shared__ __align__(16) unsigned char smem[];
+  __shared__ DevGraph sG;
+  const int n_teams = gridDim.x / team_ctas;
+  const int team = blockIdx.x / team_ctas;
+  if (team >= n_teams) return;
+  Ctx c;
+  c.rank = blockIdx.x % team_ctas;
+  c.tsize = team_ctas;
+  c.bar = bars + team * 32;
+  c.bar_target = 0;
+  c.red_slot = 0;
+  c.smem = smem;
+  for (int g = team; g < n_graphs; g += n_teams) {
+    __syncthreads();
+    const int* src = reinterpret_cast<const int*>(graphs + g);
+    int* dst = reinterpret_cast<int*>(&sG);
+    for (int i = threadIdx.x; i < (int)(sizeof(DevGraph) / sizeof(int)); i += kThreads) dst[i] = src[i];
+    __syncthreads();
+    run_graph(sG, c);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host engine
+// ---------------------------------------------------------------------------------------------
+thread_local std::string g_err;
+
+#define CUDA_OK(call)                                                                      \
+  do {                                                                                     \
+    cudaError_t e__ = (call);                                                              \
+    if (e__ != cudaSuccess) {                                                              \
+      g_err = std::string(#call) + ": " + cudaGetErrorString(e__);                         \
+      return -1;                                                                           \
+    }                                                                                      \
+  } while (0)
+
+struct Solver {
+  int device = 0;
+  Graph g;
+  pus_properties prop;
+  int robust_kind = 0;
+  double robust_b = 1.0;
+  pus_solver_options opt;
+  Compiled c;
+  uint64_t compiled_topo = 0;
+  bool meas_dirty = true;
+  bool uploaded = false;
+  int step = 0;
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  std::vector<void*> allocs;
+  std::map<std::string, std::pair<double*, size_t>> named;  // debug access to double buffers
+  DevGraph hd;
+  DevGraph* d_graph = nullptr;
+  LmResult* d_res = nullptr;
+  LmTrace* d_trace = nullptr;
+  unsigned* d_bar = nullptr;
+  LmResult res;
+  LmTrace trace;
+  pus_stats stats;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  int num_sms = 0;
+  int last_acinv = 0;
+
+  Solver() {
+    std::memset(&prop, 0, sizeof(prop));
+    prop.method = 0; prop.epsilon2 = 1e-2; prop.epsilon_abs = 1e-3; prop.epsilon_rel = 1e-5; prop.max_iterations = 500;
+    prop.lm_lambda0 = 1e-6; prop.lm_lambda_factor = 10.; prop.mod_update = 1; prop.mod_batch = 100; prop.mod_solve = 1;
+    std::memset(&opt, 0, sizeof(opt));
+    opt.pcg_rel_tol = 1e-10; opt.pcg_max_iter = 2000;
+    std::memset(&stats, 0, sizeof(stats));
+    std::memset(&res, 0, sizeof(res));
+    std::memset(&hd, 0, sizeof(hd));
+    trace_n = 0;
+  }
+  int trace_n;
+
+  void free_device() {
+    for (void* p : allocs) cudaFree(p);
+    allocs.clear();
+    named.clear();
+    uploaded = false;
+    compiled_topo = 0;
+  }
+  template <typename T>
+  int dalloc(T** out, size_t n, const char* name = nullptr) {
+    void* p = nullptr;
+    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    CUDA_OK(cudaMalloc(&p, bytes));
+    allocs.push_back(p);
+    *out = reinterpret_cast<T*>(p);
+    if (name) named[name] = std::make_pair(reinterpret_cast<double*>(p), n);
+    return 0;
+  }
+  template <typename T>
+  int dupload(const T** out, const std::vector<T>& v, long long* bytes) {
+    T* p = nullptr;
+    if (dalloc(&p, v.size()) < 0) return -1;
+    if (!v.empty()) CUDA_OK(cudaMemcpyAsync(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice, stream));
+    *bytes += (long long)(v.size() * sizeof(T));
+    *out = p;
+    return 0;
+  }
+};
+
+static int ensure_device(Solver* s) {
+  int ndev = 0;
+  cudaError_t de = cudaGetDeviceCount(&ndev);
+  if (de != cudaSuccess || ndev <= 0) {
+    g_err = std::string("no CUDA device available (") + cudaGetErrorString(de) + "); libpopup_gpu has no CPU fallback";
+    return -1;
+  }
+  if (s->device >= ndev) { g_err = "bad device ordinal"; return -1; }
+  CUDA_OK(cudaSetDevice(s->device));
+  if (!s->stream && !s->own_stream) {
+    CUDA_OK(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    s->own_stream = true;
+  }
+  if (!s->ev0) { CUDA_OK(cudaEventCreate(&s->ev0)); CUDA_OK(cudaEventCreate(&s->ev1)); }
+  if (!s->num_sms) {
+    cudaDeviceProp p;
+    CUDA_OK(cudaGetDeviceProperties(&p, s->device));
+    s->num_sms = p.multiProcessorCount;
+    CUDA_OK(cudaFuncSetAttribute(lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+  }
+  return 0;
+}
+
+// (re)build the HBM image of the graph.  Topology arrays are re-uploaded only after a structural edit;
+// vertex values always; measurements when pus_set_measurement touched them.
+static int upload(Solver* s) {
+  if (ensure_device(s) < 0) return -1;
+  cudaEvent_t e0 = s->ev0, e1 = s->ev1;
+  long long bytes = 0;
+  CUDA_OK(cudaEventRecord(e0, s->stream));
+  const bool rebuild = (s->compiled_topo != s->g.topo_version) || !s->uploaded;
+  if (rebuild) {
+    s->free_device();
+    std::string err;
+    if (!compile_graph(s->g, s->c, err)) { g_err = err; return -1; }
+    const Compiled& c = s->c;
+    if (kSmRc + 6 * c.nc * 8 > kSmemBytes) { g_err = "graph too large for the coarse-space shared-memory buffer"; return -1; }
+    DevGraph& d = s->hd;
+    std::memset(&d, 0, sizeof(d));
+    d.N = c.N; d.M = c.M; d.Epl = c.Epl; d.Epf = c.Epf; d.Elp = c.Elp; d.ntile = c.ntile; d.nblk = c.nblk; d.nc = c.nc;
+    d.SP = kCoarseSpacing; d.n_upart = c.n_upart; d.n_ypart = c.n_ypart; d.nce = c.nce; d.ngrp = c.ngrp;
+#define UP(field) if (s->dupload(&d.field, c.field, &bytes) < 0) return -1
+    UP(pp_pose); UP(pp_plane); UP(pp_ptr); UP(pm2pl); UP(pm_part); UP(ypart_ptr); UP(pp_meas); UP(pp_sinf);
+    UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr);
+    UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pf_meas); UP(pf_sinf);
+    UP(lp_plane); UP(linc_ptr); UP(linc); UP(lp_meas); UP(lp_sinf);
+    UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem);
+    UP(ce_ptr); UP(ce_node); UP(ce_plane); UP(ce_lo); UP(ce_hi); UP(n2ce_ptr); UP(n2ce);
+#undef UP
+    const size_t N = c.N, M = c.M, E = c.Epl, T = c.ntile;
+#define AL(field, n, name) if (s->dalloc(&d.field, (size_t)(n), name) < 0) return -1
+    AL(pose_lin, N * 7, "pose_lin"); AL(pose_trial, N * 7, "pose_trial"); AL(pose_init, N * 7, "pose_init");
+    AL(plane_lin, M * 4, "plane_lin"); AL(plane_trial, M * 4, "plane_trial"); AL(plane_init, M * 4, "plane_init");
+    AL(W, T * kWStride, "Wtiles"); AL(Wt, T * kWStride, "Wttiles"); AL(JP, E * 21, "JP"); AL(JL, E * 12, "JL");
+    AL(PF, (size_t)c.Epf * 120, "PF"); AL(LP, (size_t)c.Elp * 12, "LP");
+    AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
+    AL(vl, M * 3, "vl"); AL(dl, M * 3, "dl"); AL(upart, (size_t)c.n_upart * 3, "upart"); AL(ypart, (size_t)c.n_ypart * 6, "ypart");
+    AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc");
+    AL(Ac[0], (size_t)36 * c.nc * c.nc, "Ac0"); AL(Ac[1], (size_t)36 * c.nc * c.nc, "Ac1");
+    AL(x, N * 6, "x"); AL(r, N * 6, "r"); AL(z, N * 6, "z"); AL(q, N * 6, "q"); AL(b, N * 6, "b");
+    AL(pv[0], N * 6, "pv0"); AL(pv[1], N * 6, "pv1");
+    AL(rcpart[0], (size_t)c.nblk * 12, "rcpart0"); AL(rcpart[1], (size_t)c.nblk * 12, "rcpart1"); AL(qcpart, (size_t)c.nblk * 12, "qcpart");
+    AL(red, (size_t)4 * 4 * 1024, "red");
+#undef AL
+    CUDA_OK(cudaMemsetAsync(d.W, 0, T * kWStride * sizeof(double), s->stream));
+    CUDA_OK(cudaMemsetAsync(d.Wt, 0, T * kWStride * sizeof(double), s->stream));
+    if (s->dalloc(&s->d_graph, 1) < 0 || s->dalloc(&s->d_res, 1) < 0 || s->dalloc(&s->d_trace, 1) < 0 ||
+        s->dalloc(&s->d_bar, 32 * 1024) < 0)
+      return -1;
+    d.res = s->d_res; d.trace = s->d_trace;
+    s->compiled_topo = s->g.topo_version;
+    s->meas_dirty = false;
+  } else {
+    // values / measurements only
+    Compiled& c = s->c;
+    for (int p = 0; p < c.N; p++) std::memcpy(&c.pose_val[(size_t)p * 7], s->g.nodes[c.pose_node[p]].v, 7 * sizeof(double));
+    for (int l = 0; l < c.M; l++) std::memcpy(&c.plane_val[(size_t)l * 4], s->g.nodes[c.plane_node[l]].v, 4 * sizeof(double));
+    if (s->meas_dirty) {
+      for (int e = 0; e < c.Epl; e++) std::memcpy(&c.pp_meas[(size_t)e * 4], s->g.factors[c.pp_fid[e]].meas, 4 * sizeof(double));
+      for (int f = 0; f < c.Epf; f++) std::memcpy(&c.pf_meas[(size_t)f * 6], s->g.factors[c.pf_fid[f]].meas, 6 * sizeof(double));
+      for (int f = 0; f < c.Elp; f++) std::memcpy(&c.lp_meas[(size_t)f * 4], s->g.factors[c.lp_fid[f]].meas, 4 * sizeof(double));
+      if (c.Epl) CUDA_OK(cudaMemcpyAsync(const_cast<double*>(s->hd.pp_meas), c.pp_meas.data(), c.pp_meas.size() * 8, cudaMemcpyHostToDevice, s->stream));
+      if (c.Epf) CUDA_OK(cudaMemcpyAsync(const_cast<double*>(s->hd.pf_meas), c.pf_meas.data(), c.pf_meas.size() * 8, cudaMemcpyHostToDevice, s->stream));
+      if (c.Elp) CUDA_OK(cudaMemcpyAsync(const_cast<double*>(s->hd.lp_meas), c.lp_meas.data(), c.lp_meas.size() * 8, cudaMemcpyHostToDevice, s->stream));
+      bytes += (long long)(c.pp_meas.size() + c.pf_meas.size() + c.lp_meas.size()) * 8;
+      s->meas_dirty = false;
+    }
+  }
+  const Compiled& c = s->c;
+  if (c.N) {
+    CUDA_OK(cudaMemcpyAsync(s->hd.pose_init, c.pose_val.data(), c.pose_val.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_OK(cudaMemcpyAsync(s->hd.pose_lin, s->hd.pose_init, c.pose_val.size() * 8, cudaMemcpyDeviceToDevice, s->stream));
+  }
+  if (c.M) {
+    CUDA_OK(cudaMemcpyAsync(s->hd.plane_init, c.plane_val.data(), c.plane_val.size() * 8, cudaMemcpyHostToDevice, s->stream));
+    CUDA_OK(cudaMemcpyAsync(s->hd.plane_lin, s->hd.plane_init, c.plane_val.size() * 8, cudaMemcpyDeviceToDevice, s->stream));
+  }
+  bytes += (long long)(c.pose_val.size() + c.plane_val.size()) * 8;
+  CUDA_OK(cudaEventRecord(e1, s->stream));
+  CUDA_OK(cudaEventSynchronize(e1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, e0, e1));
+  s->stats.h2d_ms = ms;
+  s->stats.h2d_bytes = bytes;
+  s->uploaded = true;
+  return 0;
+}
+
+static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int debug_stage, double debug_lambda) {
+  p.method = s->prop.method; p.eps2 = s->prop.epsilon2; p.eps_abs = s->prop.epsilon_abs; p.eps_rel = s->prop.epsilon_rel;
+  p.max_iter = s->prop.max_iterations; p.lambda0 = s->prop.lm_lambda0; p.lambda_factor = s->prop.lm_lambda_factor;
+  p.robust_kind = s->robust_kind; p.robust_b = s->robust_b;
+  p.pcg_tol = s->opt.pcg_rel_tol; p.pcg_max_iter = s->opt.pcg_max_iter;
+  p.mode = mode; p.debug_stage = debug_stage; p.debug_lambda = debug_lambda; p.restore_init = restore_init;
+}
+
+static int auto_team(const Solver* s, int limit) {
+  if (s->opt.team_ctas > 0) return std::min(std::max(1, s->opt.team_ctas), limit);
+  int need = std::max((s->c.ntile + kWarps - 1) / kWarps, (s->c.nblk + kSlots - 1) / kSlots);
+  return std::min(std::max(need, 1), limit);
+}
+
+// launch the persistent kernel over `n` solvers (all on the device / stream of the first)
+static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stage, double debug_lambda) {
+  Solver* s0 = ss[0];
+  if (ensure_device(s0) < 0) return -1;
+  for (int i = 0; i < n; i++) {
+    if (!ss[i]->uploaded) { g_err = "graph not uploaded"; return -1; }
+    if (ss[i]->device != s0->device) { g_err = "all graphs of a batch must live on one device"; return -1; }
+  }
+  int per_sm = 0;
+  CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lm_kernel, kThreads, kSmemBytes));
+  if (per_sm < 1) { g_err = "lm_kernel does not fit on an SM"; return -1; }
+  const int max_ctas = s0->num_sms * 1;
+  int team = 1, grid = 1;
+  if (n == 1) {
+    team = auto_team(s0, max_ctas);
+    grid = team;
+  } else {
+    int share = std::max(1, max_ctas / n);
+    int need = 1;
+    for (int i = 0; i < n; i++) need = std::max(need, auto_team(ss[i], max_ctas));
+    team = std::min(share, need);
+    int teams = std::min(n, max_ctas / team);
+    grid = teams * team;
+  }
+  // per-graph parameter blocks
+  std::vector<DevGraph> hg(n);
+  for (int i = 0; i < n; i++) {
+    fill_params(ss[i], ss[i]->hd.prm, mode, restore_init, debug_stage, debug_lambda);
+    hg[i] = ss[i]->hd;
+  }
+  DevGraph* d_graphs = s0->d_graph;
+  DevGraph* d_tmp = nullptr;
+  if (n > 1) {
+    CUDA_OK(cudaMalloc(&d_tmp, sizeof(DevGraph) * n));
+    d_graphs = d_tmp;
+  }
+  CUDA_OK(cudaMemcpyAsync(d_graphs, hg.data(), sizeof(DevGraph) * n, cudaMemcpyHostToDevice, s0->stream));
+  CUDA_OK(cudaMemsetAsync(s0->d_bar, 0, 32 * 1024 * sizeof(unsigned), s0->stream));
+  CUDA_OK(cudaEventRecord(s0->ev0, s0->stream));
+  const DevGraph* a0 = d_graphs;
+  int a1 = n, a2 = team;
+  unsigned* a3 = s0->d_bar;
+  void* args[] = {(void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3};
+  cudaError_t le = cudaLaunchCooperativeKernel((void*)lm_kernel, dim3(grid), dim3(kThreads), args, kSmemBytes, s0->stream);
+  if (le != cudaSuccess) { g_err = std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(le); if (d_tmp) cudaFree(d_tmp); return -1; }
+  CUDA_OK(cudaEventRecord(s0->ev1, s0->stream));
+  cudaError_t se = cudaEventSynchronize(s0->ev1);
+  if (d_tmp) cudaFree(d_tmp);
+  if (se != cudaSuccess) { g_err = std::string("lm_kernel: ") + cudaGetErrorString(se); return -1; }
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, s0->ev0, s0->ev1));
+  for (int i = 0; i < n; i++) {
+    Solver* s = ss[i];
+    CUDA_OK(cudaMemcpyAsync(&s->res, s->d_res, sizeof(LmResult), cudaMemcpyDeviceToHost, s0->stream));
+    CUDA_OK(cudaStreamSynchronize(s0->stream));
+    pus_stats& st = s->stats;
+    st.lm_iterations = s->res.iterations; st.accepted = s->res.accepted; st.relinearizations = s->res.relin;
+    st.chi2_evals = s->res.chi2_evals; st.pcg_iterations = s->res.pcg_iters; st.chi2_initial = s->res.chi2_initial;
+    st.chi2_final = s->res.chi2_final; st.kernel_ms = ms; st.n_poses = s->c.N; st.n_planes = s->c.M; st.n_pose_plane = s->c.Epl;
+    int npr = 0;
+    for (int f = 0; f < s->c.Epf; f++) npr += s->c.pf_j[f] < 0;
+    st.n_pose_prior = npr; st.n_odometry = s->c.Epf - npr; st.n_plane_prior = s->c.Elp;
+    st.gpu_launches = 1; st.grid_ctas = grid; st.block_threads = kThreads;
+    for (int k = 0; k < 8; k++) st.phase_ms[k] = s->res.phase_ns[k] * 1e-6;
+    s->last_acinv = s->res.status;
+  }
+  return 0;
+}
+
+static int download(Solver** ss, int n) {
+  Solver* s0 = ss[0];
+  CUDA_OK(cudaSetDevice(s0->device));
+  CUDA_OK(cudaEventRecord(s0->ev0, s0->stream));
+  long long bytes = 0;
+  for (int i = 0; i < n; i++) {
+    Solver* s = ss[i];
+    Compiled& c = s->c;
+    if (c.N) CUDA_OK(cudaMemcpyAsync(c.pose_val.data(), s->hd.pose_lin, c.pose_val.size() * 8, cudaMemcpyDeviceToHost, s0->stream));
+    if (c.M) CUDA_OK(cudaMemcpyAsync(c.plane_val.data(), s->hd.plane_lin, c.plane_val.size() * 8, cudaMemcpyDeviceToHost, s0->stream));
+    CUDA_OK(cudaMemcpyAsync(&s->trace, s->d_trace, sizeof(LmTrace), cudaMemcpyDeviceToHost, s0->stream));
+    bytes += (long long)(c.pose_val.size() + c.plane_val.size()) * 8;
+  }
+  CUDA_OK(cudaEventRecord(s0->ev1, s0->stream));
+  CUDA_OK(cudaEventSynchronize(s0->ev1));
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, s0->ev0, s0->ev1));
+  for (int i = 0; i < n; i++) {
+    Solver* s = ss[i];
+    Compiled& c = s->c;
+    for (int p = 0; p < c.N; p++) std::memcpy(s->g.nodes[c.pose_node[p]].v, &c.pose_val[(size_t)p * 7], 7 * sizeof(double));
+    for (int l = 0; l < c.M; l++) std::memcpy(s->g.nodes[c.plane_node[l]].v, &c.plane_val[(size_t)l * 4], 4 * sizeof(double));
+    s->trace_n = s->res.trace_n;
+    s->stats.d2h_ms = ms;
+    s->stats.d2h_bytes = bytes / n;
+  }
+  return 0;
+}
+
+}  // namespace pus
+
+// ---------------------------------------------------------------------------------------------
+// C-ABI
+// ---------------------------------------------------------------------------------------------
+using namespace pus;
+#define SV(h) (reinterpret_cast<Solver*>(h))
+#define NEED(h) if (!(h)) { g_err = "null handle"; return -1; }
+
+extern "C" {
+
+const char* pus_last_error(void) { return g_err.c_str(); }
+
+// The handle itself (graph container, ids, values) is host state; the device is bound lazily by the
+// first upload / optimise call, which fails loudly when no CUDA device is usable (no CPU fallback).
+int pus_create(int device, pus_handle* out) {
+  if (device < 0) { g_err = "bad device ordinal"; return -1; }
+  Solver* s = new Solver();
+  s->device = device;
+  *out = s;
+  return 0;
+}
+int pus_destroy(pus_handle h) {
+  NEED(h);
+  Solver* s = SV(h);
+  cudaSetDevice(s->device);
+  s->free_device();
+  if (s->ev0) cudaEventDestroy(s->ev0);
+  if (s->ev1) cudaEventDestroy(s->ev1);
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  delete s;
+  return 0;
+}
+int pus_set_stream(pus_handle h, void* st) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (s->own_stream && s->stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
+  s->stream = reinterpret_cast<cudaStream_t>(st);
+  if (!st) { s->stream = nullptr; }
+  else s->own_stream = false;
+  if (!st) s->own_stream = false;
+  return 0;
+}
+
+int pus_add_pose(pus_handle h, const double* v) { NEED(h); return SV(h)->g.add_node(NODE_POSE, v); }
+int pus_add_plane(pus_handle h, const double* v) { NEED(h); return SV(h)->g.add_node(NODE_PLANE, v); }
+int pus_add_poses(pus_handle h, int n, const double* v, int* out) {
+  NEED(h);
+  int first = -1;
+  for (int i = 0; i < n; i++) { int id = SV(h)->g.add_node(NODE_POSE, v ? v + 7 * i : nullptr); if (!i) first = id; if (out) out[i] = id; }
+  return first;
+}
+int pus_add_planes(pus_handle h, int n, const double* v, int* out) {
+  NEED(h);
+  int first = -1;
+  for (int i = 0; i < n; i++) { int id = SV(h)->g.add_node(NODE_PLANE, v ? v + 4 * i : nullptr); if (!i) first = id; if (out) out[i] = id; }
+  return first;
+}
+int pus_init_pose(pus_handle h, int id, const double* v) {
+  NEED(h);
+  if (!SV(h)->g.ok_node(id, NODE_POSE)) { g_err = "bad pose id"; return -1; }
+  SV(h)->g.init_node(id, v); return 0;
+}
+int pus_init_plane(pus_handle h, int id, const double* v) {
+  NEED(h);
+  if (!SV(h)->g.ok_node(id, NODE_PLANE)) { g_err = "bad plane id"; return -1; }
+  SV(h)->g.init_node(id, v); return 0;
+}
+int pus_get_pose(pus_handle h, int id, double* out) {
+  NEED(h);
+  if (!SV(h)->g.ok_node(id, NODE_POSE)) { g_err = "bad pose id"; return -1; }
+  std::memcpy(out, SV(h)->g.nodes[id].v, 7 * sizeof(double)); return 0;
+}
+int pus_get_plane(pus_handle h, int id, double* out) {
+  NEED(h);
+  if (!SV(h)->g.ok_node(id, NODE_PLANE)) { g_err = "bad plane id"; return -1; }
+  std::memcpy(out, SV(h)->g.nodes[id].v, 4 * sizeof(double)); return 0;
+}
+int pus_get_poses(pus_handle h, int n, const int* ids, double* out) {
+  for (int i = 0; i < n; i++) if (pus_get_pose(h, ids[i], out + 7 * i) < 0) return -1;
+  return 0;
+}
+int pus_get_planes(pus_handle h, int n, const int* ids, double* out) {
+  for (int i = 0; i < n; i++) if (pus_get_plane(h, ids[i], out + 4 * i) < 0) return -1;
+  return 0;
+}
+
+static int chk(Solver* s, int r) { if (r < 0) g_err = s->g.err; return r; }
+int pus_add_pose_prior(pus_handle h, int p, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_pose_prior(p, m, si)); }
+int pus_add_odometry(pus_handle h, int a, int b, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_odometry(a, b, m, si)); }
+int pus_add_pose_plane(pus_handle h, int p, int l, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_pose_plane(p, l, m, si)); }
+int pus_add_plane_prior(pus_handle h, int l, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_plane_prior(l, m, si)); }
+int pus_add_odometry_bulk(pus_handle h, int n, const int* a, const int* b, const double* m, const double* si, int* out) {
+  NEED(h);
+  int first = -1;
+  for (int i = 0; i < n; i++) {
+    int f = chk(SV(h), SV(h)->g.add_odometry(a[i], b[i], m + 6 * i, si + 21 * i));
+    if (f < 0) return f;
+    if (!i) first = f;
+    if (out) out[i] = f;
+  }
+  return first;
+}
+int pus_add_pose_plane_bulk(pus_handle h, int n, const int* a, const int* b, const double* m, const double* si, int* out) {
+  NEED(h);
+  int first = -1;
+  for (int i = 0; i < n; i++) {
+    int f = chk(SV(h), SV(h)->g.add_pose_plane(a[i], b[i], m + 4 * i, si + 6 * i));
+    if (f < 0) return f;
+    if (!i) first = f;
+    if (out) out[i] = f;
+  }
+  return first;
+}
+int pus_set_measurement(pus_handle h, int fid, const double* m) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (!s->g.ok_factor(fid)) { g_err = "bad factor id"; return -1; }
+  HFactor& f = s->g.factors[fid];
+  if (f.dim == 3) { std::memcpy(f.meas, m, 4 * sizeof(double)); normalize4(f.meas); }
+  else std::memcpy(f.meas, m, 6 * sizeof(double));
+  s->meas_dirty = true;
+  return 0;
+}
+int pus_get_measurement(pus_handle h, int fid, double* m) {
+  NEED(h);
+  if (!SV(h)->g.ok_factor(fid)) { g_err = "bad factor id"; return -1; }
+  const HFactor& f = SV(h)->g.factors[fid];
+  std::memcpy(m, f.meas, (f.dim == 3 ? 4 : 6) * sizeof(double)); return 0;
+}
+int pus_remove_factor(pus_handle h, int fid) {
+  NEED(h);
+  if (!SV(h)->g.ok_factor(fid)) { g_err = "bad factor id"; return -1; }
+  SV(h)->g.remove_factor(fid); return 0;
+}
+int pus_remove_node(pus_handle h, int id) {
+  NEED(h);
+  if (id < 0 || id >= (int)SV(h)->g.nodes.size() || !SV(h)->g.nodes[id].alive) { g_err = "bad node id"; return -1; }
+  SV(h)->g.remove_node(id); return 0;
+}
+int pus_num_nodes(pus_handle h) { NEED(h); return SV(h)->g.num_nodes(); }
+int pus_num_factors(pus_handle h) { NEED(h); return SV(h)->g.num_factors(); }
+int pus_factor_nodes(pus_handle h, int fid, int* out2) {
+  NEED(h);
+  if (!SV(h)->g.ok_factor(fid)) { g_err = "bad factor id"; return -1; }
+  const HFactor& f = SV(h)->g.factors[fid];
+  for (int k = 0; k < f.n_nodes; k++) out2[k] = f.nodes[k];
+  return f.n_nodes;
+}
+int pus_node_factors(pus_handle h, int id, int* out, int cap) {
+  NEED(h);
+  const Graph& g = SV(h)->g;
+  if (id < 0 || id >= (int)g.nodes.size() || !g.nodes[id].alive) { g_err = "bad node id"; return -1; }
+  int c = 0;
+  for (size_t i = 0; i < g.factors.size(); i++) {
+    const HFactor& f = g.factors[i];
+    if (!f.alive) continue;
+    for (int k = 0; k < f.n_nodes; k++) if (f.nodes[k] == id) { if (c < cap) out[c] = (int)i; c++; break; }
+  }
+  return c;
+}
+int pus_node_start(pus_handle h, int id) { if (!h) return -1; return SV(h)->g.node_start(id); }
+int pus_factor_row(pus_handle h, int fid) { if (!h) return -1; return SV(h)->g.factor_row(fid); }
+
+int pus_get_properties(pus_handle h, pus_properties* out) { NEED(h); *out = SV(h)->prop; return 0; }
+int pus_set_properties(pus_handle h, const pus_properties* in) { NEED(h); SV(h)->prop = *in; return 0; }
+int pus_set_robust(pus_handle h, int kind, double b) {
+  NEED(h);
+  if (kind < 0 || kind > 2 || !(b > 0)) { g_err = "bad robust cost"; return -1; }
+  SV(h)->robust_kind = kind; SV(h)->robust_b = b; return 0;
+}
+int pus_get_solver_options(pus_handle h, pus_solver_options* out) { NEED(h); *out = SV(h)->opt; return 0; }
+int pus_set_solver_options(pus_handle h, const pus_solver_options* in) { NEED(h); SV(h)->opt = *in; return 0; }
+
+int pus_upload(pus_handle h) { NEED(h); return upload(SV(h)); }
+int pus_upload_many(pus_handle* hs, int n) {
+  for (int i = 0; i < n; i++) if (upload(SV(hs[i])) < 0) return -1;
+  return 0;
+}
+static int solve_many(pus_handle* hs, int n, int* iters, int mode, int restore) {
+  if (n <= 0) return 0;
+  std::vector<Solver*> ss(n);
+  for (int i = 0; i < n; i++) {
+    ss[i] = SV(hs[i]);
+    if (i > 0) { ss[i]->stream = ss[0]->stream; }
+  }
+  if (launch(ss.data(), n, mode, restore, 0, 0.0) < 0) return -1;
+  if (iters) for (int i = 0; i < n; i++) iters[i] = ss[i]->res.iterations;
+  return 0;
+}
+int pus_solve_resident(pus_handle h, int* iters) { NEED(h); return solve_many(&h, 1, iters, MODE_BATCH, 1); }
+int pus_solve_resident_many(pus_handle* hs, int n, int* iters) {
+  if (n > 1) {  // all graphs ride on the first handle's stream
+    Solver* s0 = SV(hs[0]);
+    if (ensure_device(s0) < 0) return -1;
+  }
+  return solve_many(hs, n, iters, MODE_BATCH, 1);
+}
+int pus_download(pus_handle h) { NEED(h); Solver* s = SV(h); return download(&s, 1); }
+int pus_download_many(pus_handle* hs, int n) {
+  std::vector<Solver*> ss(n);
+  for (int i = 0; i < n; i++) ss[i] = SV(hs[i]);
+  return n ? download(ss.data(), n) : 0;
+}
+
+int pus_batch_optimize(pus_handle h, int* iters) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (upload(s) < 0) return -1;
+  if (solve_many(&h, 1, iters, MODE_BATCH, 0) < 0) return -1;
+  return download(&s, 1);
+}
+int pus_batch_optimize_many(pus_handle* hs, int n, int* iters) {
+  if (n <= 0) return 0;
+  Solver* s0 = SV(hs[0]);
+  if (ensure_device(s0) < 0) return -1;
+  for (int i = 1; i < n; i++) {
+    Solver* s = SV(hs[i]);
+    if (s->own_stream && s->stream && s->stream != s0->stream) { cudaStreamDestroy(s->stream); }
+    s->own_stream = false;
+    s->stream = s0->stream;
+  }
+  if (pus_upload_many(hs, n) < 0) return -1;
+  if (solve_many(hs, n, iters, MODE_BATCH, 0) < 0) return -1;
+  return pus_download_many(hs, n);
+}
+// Slam::update (Slam.cpp:157-196). PPS runs with mod_batch = 1 => every call is the batch step
+// (relinearise + one Gauss-Newton step). Other settings would need iSAM's Givens incremental path.
+int pus_update(pus_handle h) {
+  NEED(h);
+  Solver* s = SV(h);
+  int rc = 0;
+  if (s->step % std::max(1, s->prop.mod_update) == 0) {
+    if (s->step % std::max(1, s->prop.mod_batch) == 0) {
+      if (upload(s) < 0) return -1;
+      if (solve_many(&h, 1, nullptr, MODE_UPDATE, 0) < 0) return -1;
+      rc = download(&s, 1);
+    } else {
+      g_err = "pus_update: incremental (Givens) steps are not implemented; set mod_batch = 1 as pop_planar_slam does";
+      rc = -1;
+    }
+  }
+  s->step++;
+  return rc;
+}
+int pus_chi2(pus_handle h, double* out) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (upload(s) < 0) return -1;
+  if (solve_many(&h, 1, nullptr, MODE_CHI2, 0) < 0) return -1;
+  *out = s->res.chi2_final;
+  return 0;
+}
+
+int pus_get_stats(pus_handle h, pus_stats* out) { NEED(h); *out = SV(h)->stats; return 0; }
+int pus_get_trace(pus_handle h, int cap, double* lambda, double* e_new, double* e_before, double* dn, int* acc, int* pcg) {
+  NEED(h);
+  Solver* s = SV(h);
+  int n = s->trace_n;
+  for (int i = 0; i < n && i < cap; i++) {
+    if (lambda) lambda[i] = s->trace.lambda[i];
+    if (e_new) e_new[i] = s->trace.chi2_new[i];
+    if (e_before) e_before[i] = s->trace.chi2_before[i];
+    if (dn) dn[i] = s->trace.delta_norm[i];
+    if (acc) acc[i] = s->trace.accepted[i];
+    if (pcg) pcg[i] = s->trace.pcg[i];
+  }
+  return n;
+}
+
+// ---- debug hooks ----
+long long pus_debug_fetch(pus_handle h, const char* name, double* out, long long cap) {
+  NEED(h);
+  Solver* s = SV(h);
+  const Compiled& c = s->c;
+  std::string nm(name);
+  cudaSetDevice(s->device);
+  auto ints = [&](const std::vector<int>& v) -> long long {
+    if ((long long)v.size() <= cap) for (size_t i = 0; i < v.size(); i++) out[i] = v[i];
+    return (long long)v.size();
+  };
+  if (nm == "pp_fid") return ints(c.pp_fid);
+  if (nm == "pp_pose") return ints(c.pp_pose);
+  if (nm == "pp_plane") return ints(c.pp_plane);
+  if (nm == "pf_fid") return ints(c.pf_fid);
+  if (nm == "pose_node") return ints(c.pose_node);
+  if (nm == "plane_node") return ints(c.plane_node);
+  if (nm == "pl2pm") return ints(c.pl2pm);
+  if (nm == "pm_part") return ints(c.pm_part);
+  if (nm == "pl_part") return ints(c.pl_part);
+  if (nm == "ypart_ptr") return ints(c.ypart_ptr);
+  if (nm == "upart_ptr") return ints(c.upart_ptr);
+  if (nm == "ce_node") return ints(c.ce_node);
+  if (nm == "ce_plane") return ints(c.ce_plane);
+  if (nm == "ce_lo") return ints(c.ce_lo);
+  if (nm == "ce_hi") return ints(c.ce_hi);
+  if (nm == "grp_plane") return ints(c.grp_plane);
+  if (nm == "grp_mem") return ints(c.grp_mem);
+  if (nm == "grp_mem_ptr") return ints(c.grp_mem_ptr);
+  if (nm == "blk_grp_ptr") return ints(c.blk_grp_ptr);
+  if (nm == "dims") {
+    double d[10] = {(double)c.N, (double)c.M, (double)c.Epl, (double)c.Epf, (double)c.Elp, (double)c.ntile, (double)c.nblk, (double)c.nc, (double)c.nce, (double)c.ngrp};
+    if (cap >= 10) std::memcpy(out, d, sizeof(d));
+    return 10;
+  }
+  if (!s->uploaded) { g_err = "nothing uploaded"; return -1; }
+  if (nm == "W" || nm == "Wt") {  // de-tiled: [Epl][18] in pose-major (W) or plane-major (Wt) order
+    size_t n = (size_t)c.ntile * kWStride;
+    std::vector<double> tmp(n);
+    if (cudaMemcpy(tmp.data(), nm == "W" ? s->hd.W : s->hd.Wt, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { g_err = "memcpy"; return -1; }
+    long long cnt = (long long)c.Epl * 18;
+    if (cnt <= cap)
+      for (int e = 0; e < c.Epl; e++)
+        for (int k = 0; k < 18; k++) out[(size_t)e * 18 + k] = tmp[(size_t)(e >> 5) * kWStride + k * 32 + (e & 31)];
+    return cnt;
+  }
+  if (nm == "Acinv") nm = s->last_acinv ? "Ac1" : "Ac0";
+  auto it = s->named.find(nm);
+  if (it == s->named.end()) { g_err = "unknown buffer " + nm; return -1; }
+  long long cnt = (long long)it->second.second;
+  if (cnt <= cap && cnt > 0)
+    if (cudaMemcpy(out, it->second.first, (size_t)cnt * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { g_err = "memcpy"; return -1; }
+  return cnt;
+}
+long long pus_debug_store(pus_handle h, const char* name, const double* in, long long count) {
+  NEED(h);
+  Solver* s = SV(h);
+  cudaSetDevice(s->device);
+  auto it = s->named.find(name);
+  if (it == s->named.end()) { g_err = std::string("unknown buffer ") + name; return -1; }
+  if (count > (long long)it->second.second) { g_err = "too many elements"; return -1; }
+  if (cudaMemcpy(it->second.first, in, (size_t)count * 8, cudaMemcpyHostToDevice) != cudaSuccess) { g_err = "memcpy"; return -1; }
+  return count;
+}
+int pus_debug_run_stage(pus_handle h, int stage, double lambda) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (!s->uploaded) { g_err = "call pus_upload first"; return -1; }
+  return launch(&s, 1, MODE_DEBUG, 0, stage, lambda);
+}
+
+// host-only hook for the CPU test-suite: compile the graph and report array sizes without touching a GPU
+int pus_debug_compile(pus_handle h) {
+  NEED(h);
+  Solver* s = SV(h);
+  std::string err;
+  if (!compile_graph(s->g, s->c, err)) { g_err = err; return -1; }
+  return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,352 @@
+// pus_graph.hpp -- host side of the drop-in boundary: the factor-graph container that mirrors
+// isam::Slam's graph bookkeeping, and the "compiler" that flattens it into the HBM layout the
+// CUDA kernels sweep.  Pure C++ (no CUDA), so it is unit-tested on the CPU.
+//
+// Reference semantics reproduced (paths relative to the reference checkout;
+// ISAM = pop_planar_slam/Thirdparty/isam, PPS = pop_planar_slam):
+//   insertion-ordered ids / lists ...... ISAM/isamlib/Slam.cpp:47-48,91-126, ISAM/include/isam/Graph.h:40-133
+//   column / row offsets ................ Slam::update_starts Slam.cpp:59-67, jacobian_partial Slam.cpp:395-432
+//   factor initialisation of nodes ...... slam3d.h:75-80,123-137 ; PPS/src/isam_plane3d.h:252-264,443-448
+//   measurement update .................. ISAM/include/isam/Factor.h:203-206
+#pragma once
+#include <algorithm>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "pus_math.cuh"
+
+namespace pus {
+
+enum NodeKind { NODE_POSE = 0, NODE_PLANE = 1 };
+enum FactorKind { F_POSE_PRIOR = 0, F_ODOMETRY = 1, F_POSE_PLANE = 2, F_PLANE_PRIOR = 3 };
+
+constexpr int kBlockPoses = 16;            // poses per dense preconditioner block
+constexpr int kBlockDim = 6 * kBlockPoses; // 96
+constexpr int kCoarseSpacing = 64;         // poses between coarse (hat-function) nodes; multiple of kBlockPoses
+constexpr int kTile = 32;                  // edges per warp tile
+constexpr int kWStride = 18 * kTile;       // doubles per W tile
+
+struct HNode {
+  int kind = NODE_POSE;
+  bool alive = true;
+  bool initialized = false;
+  double v[7] = {0, 0, 0, 1, 0, 0, 0};  // pose: x y z qw qx qy qz ; plane: a b c d
+};
+
+struct HFactor {
+  int kind = F_POSE_PLANE;
+  bool alive = true;
+  int nodes[2] = {-1, -1};
+  int n_nodes = 1;
+  int dim = 3;
+  double meas[6] = {0, 0, 0, 0, 0, 0};
+  double sinf[21];  // packed upper-triangular
+};
+
+struct Graph {
+  std::vector<HNode> nodes;
+  std::vector<HFactor> factors;
+  std::string err;
+  uint64_t topo_version = 1;  // bumped on any structural edit (node/factor add/remove)
+
+  bool ok_node(int id, int kind) const { return id >= 0 && id < (int)nodes.size() && nodes[id].alive && nodes[id].kind == kind; }
+  bool ok_factor(int f) const { return f >= 0 && f < (int)factors.size() && factors[f].alive; }
+
+  int add_node(int kind, const double* v) {
+    HNode n;
+    n.kind = kind;
+    if (v) {
+      if (kind == NODE_POSE) std::memcpy(n.v, v, 7 * sizeof(double));
+      else { std::memcpy(n.v, v, 4 * sizeof(double)); normalize4(n.v); }
+      n.initialized = true;
+    } else if (kind == NODE_PLANE) { n.v[0] = 1; n.v[1] = n.v[2] = n.v[3] = 0; }
+    nodes.push_back(n);
+    topo_version++;
+    return (int)nodes.size() - 1;
+  }
+  void init_node(int id, const double* v) {
+    HNode& n = nodes[id];
+    if (n.kind == NODE_POSE) std::memcpy(n.v, v, 7 * sizeof(double));
+    else { std::memcpy(n.v, v, 4 * sizeof(double)); normalize4(n.v); }
+    n.initialized = true;
+  }
+
+  int push_factor(HFactor& f) { factors.push_back(f); topo_version++; return (int)factors.size() - 1; }
+
+  int add_pose_prior(int pose, const double* m, const double* si) {
+    if (!ok_node(pose, NODE_POSE)) { err = "add_pose_prior: bad pose id"; return -1; }
+    HFactor f; f.kind = F_POSE_PRIOR; f.n_nodes = 1; f.nodes[0] = pose; f.dim = 6;
+    std::memcpy(f.meas, m, 6 * sizeof(double)); std::memcpy(f.sinf, si, 21 * sizeof(double));
+    if (!nodes[pose].initialized) { double p[7]; pose_from_xyzypr(m, p); init_node(pose, p); }  // slam3d.h:75-80
+    return push_factor(f);
+  }
+  int add_odometry(int a, int b, const double* m, const double* si) {
+    if (!ok_node(a, NODE_POSE) || !ok_node(b, NODE_POSE)) { err = "add_odometry: bad pose id"; return -1; }
+    if (!nodes[a].initialized && !nodes[b].initialized) {
+      err = "slam3d: Pose3d_Pose3d_Factor requires pose1 or pose2 to be initialized";  // slam3d.h:124-125
+      return -1;
+    }
+    HFactor f; f.kind = F_ODOMETRY; f.n_nodes = 2; f.nodes[0] = a; f.nodes[1] = b; f.dim = 6;
+    std::memcpy(f.meas, m, 6 * sizeof(double)); std::memcpy(f.sinf, si, 21 * sizeof(double));
+    double mp[7]; pose_from_xyzypr(m, mp);
+    if (!nodes[a].initialized) {            // slam3d.h:127-132: p2.oplus(z.ominus(measure))
+      double z[7] = {0, 0, 0, 1, 0, 0, 0}, inv[7], out[7];
+      pose_ominus(z, mp, inv); pose_oplus(nodes[b].v, inv, out); init_node(a, out);
+    } else if (!nodes[b].initialized) {     // slam3d.h:133-137: p1.oplus(measure)
+      double out[7]; pose_oplus(nodes[a].v, mp, out); init_node(b, out);
+    }
+    return push_factor(f);
+  }
+  int add_pose_plane(int pose, int plane, const double* m, const double* si) {
+    if (!ok_node(pose, NODE_POSE) || !ok_node(plane, NODE_PLANE)) { err = "add_pose_plane: bad node id"; return -1; }
+    if (!nodes[pose].initialized) { err = "Plane3d: Pose3d_Plane3d_Factor requires pose to be initialized"; return -1; }
+    HFactor f; f.kind = F_POSE_PLANE; f.n_nodes = 2; f.nodes[0] = pose; f.nodes[1] = plane; f.dim = 3;
+    std::memcpy(f.meas, m, 4 * sizeof(double)); normalize4(f.meas);
+    std::memcpy(f.sinf, si, 6 * sizeof(double));
+    if (!nodes[plane].initialized) {        // isam_plane3d.h:256-262: measure.transform_from(p.oTw())
+      double T[16], g[4]; pose_to_Tinv(nodes[pose].v, T); plane_transform_T(T, f.meas, g); init_node(plane, g);
+    }
+    return push_factor(f);
+  }
+  int add_plane_prior(int plane, const double* m, const double* si) {
+    if (!ok_node(plane, NODE_PLANE)) { err = "add_plane_prior: bad plane id"; return -1; }
+    HFactor f; f.kind = F_PLANE_PRIOR; f.n_nodes = 1; f.nodes[0] = plane; f.dim = 3;
+    std::memcpy(f.meas, m, 4 * sizeof(double)); normalize4(f.meas);
+    std::memcpy(f.sinf, si, 6 * sizeof(double));
+    if (!nodes[plane].initialized) init_node(plane, f.meas);  // isam_plane3d.h:443-448
+    return push_factor(f);
+  }
+  void remove_factor(int f) { factors[f].alive = false; topo_version++; }
+  void remove_node(int id) {  // Slam::remove_node Slam.cpp:107-115: adjacent factors go too
+    for (auto& f : factors) {
+      if (!f.alive) continue;
+      for (int k = 0; k < f.n_nodes; k++) if (f.nodes[k] == id) { f.alive = false; break; }
+    }
+    nodes[id].alive = false;
+    topo_version++;
+  }
+  int num_nodes() const { int c = 0; for (auto& n : nodes) c += n.alive; return c; }
+  int num_factors() const { int c = 0; for (auto& f : factors) c += f.alive; return c; }
+  int node_start(int id) const {
+    if (id < 0 || id >= (int)nodes.size() || !nodes[id].alive) return -1;
+    int s = 0;
+    for (int i = 0; i < id; i++) if (nodes[i].alive) s += nodes[i].kind == NODE_POSE ? 6 : 3;
+    return s;
+  }
+  int factor_row(int fid) const {
+    if (!ok_factor(fid)) return -1;
+    int r = 0;
+    for (int i = 0; i < fid; i++) if (factors[i].alive) r += factors[i].dim;
+    return r;
+  }
+};
+
+// ------------------------------------------------------------------------------------------------
+// Flattened problem (host copy of what goes to HBM).  All index arrays are int32.
+// ------------------------------------------------------------------------------------------------
+struct Compiled {
+  int N = 0, M = 0, Epl = 0, Epf = 0, Elp = 0;
+  int ntile = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0;
+  std::vector<int> pose_node, plane_node;   // idx -> node id
+  std::vector<int> node_idx;                // node id -> idx (pose idx or plane idx), -1 dead
+  std::vector<double> pose_val, plane_val;  // [N*7], [M*4]
+  // pose-plane edges, pose-major
+  std::vector<int> pp_fid, pp_pose, pp_plane, pp_ptr, pm2pl, pm_part, ypart_ptr;
+  std::vector<double> pp_meas, pp_sinf;
+  // plane-major view
+  std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr;
+  // pose factors (prior / odometry)
+  std::vector<int> pf_fid, pf_i, pf_j, pinc_ptr, pinc;
+  std::vector<double> pf_meas, pf_sinf;
+  // plane priors
+  std::vector<int> lp_fid, lp_plane, linc_ptr, linc;
+  std::vector<double> lp_meas, lp_sinf;
+  // dense-block groups: per pose block, its edges grouped by plane
+  std::vector<int> blk_grp_ptr, grp_plane, grp_mem_ptr, grp_mem;
+  // coarse (hat) space: (plane, coarse node) pairs
+  std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
+};
+
+inline int coarse_nodes(int N) { return N <= 1 ? 1 : (N - 1 + kCoarseSpacing - 1) / kCoarseSpacing + 1; }
+
+inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
+  c = Compiled();
+  const int nn = (int)g.nodes.size();
+  c.node_idx.assign(nn, -1);
+  for (int i = 0; i < nn; i++) {
+    const HNode& n = g.nodes[i];
+    if (!n.alive) continue;
+    if (!n.initialized) { err = "node " + std::to_string(i) + " is not initialised"; return false; }
+    if (n.kind == NODE_POSE) { c.node_idx[i] = (int)c.pose_node.size(); c.pose_node.push_back(i); }
+    else { c.node_idx[i] = (int)c.plane_node.size(); c.plane_node.push_back(i); }
+  }
+  c.N = (int)c.pose_node.size(); c.M = (int)c.plane_node.size();
+  const int N = c.N, M = c.M;
+  c.pose_val.resize((size_t)N * 7); c.plane_val.resize((size_t)M * 4);
+  for (int p = 0; p < N; p++) std::memcpy(&c.pose_val[(size_t)p * 7], g.nodes[c.pose_node[p]].v, 7 * sizeof(double));
+  for (int l = 0; l < M; l++) std::memcpy(&c.plane_val[(size_t)l * 4], g.nodes[c.plane_node[l]].v, 4 * sizeof(double));
+
+  // ---- split factors ----
+  std::vector<int> ppf;  // pose-plane factor ids in insertion order
+  for (int f = 0; f < (int)g.factors.size(); f++) {
+    const HFactor& F = g.factors[f];
+    if (!F.alive) continue;
+    switch (F.kind) {
+      case F_POSE_PLANE: ppf.push_back(f); break;
+      case F_POSE_PRIOR:
+      case F_ODOMETRY:
+        c.pf_fid.push_back(f);
+        c.pf_i.push_back(c.node_idx[F.nodes[0]]);
+        c.pf_j.push_back(F.kind == F_ODOMETRY ? c.node_idx[F.nodes[1]] : -1);
+        c.pf_meas.insert(c.pf_meas.end(), F.meas, F.meas + 6);
+        c.pf_sinf.insert(c.pf_sinf.end(), F.sinf, F.sinf + 21);
+        break;
+      case F_PLANE_PRIOR:
+        c.lp_fid.push_back(f);
+        c.lp_plane.push_back(c.node_idx[F.nodes[0]]);
+        c.lp_meas.insert(c.lp_meas.end(), F.meas, F.meas + 4);
+        c.lp_sinf.insert(c.lp_sinf.end(), F.sinf, F.sinf + 6);
+        break;
+    }
+  }
+  c.Epf = (int)c.pf_fid.size(); c.Elp = (int)c.lp_fid.size();
+  // ---- pose-major ordering of the pose-plane edges (stable: insertion order within a pose) ----
+  c.Epl = (int)ppf.size();
+  const int E = c.Epl;
+  std::vector<int> order(E);
+  for (int i = 0; i < E; i++) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+    return c.node_idx[g.factors[ppf[a]].nodes[0]] < c.node_idx[g.factors[ppf[b]].nodes[0]];
+  });
+  c.pp_fid.resize(E); c.pp_pose.resize(E); c.pp_plane.resize(E);
+  c.pp_meas.resize((size_t)E * 4); c.pp_sinf.resize((size_t)E * 6);
+  c.pp_ptr.assign(N + 1, 0);
+  for (int e = 0; e < E; e++) {
+    const HFactor& F = g.factors[ppf[order[e]]];
+    c.pp_fid[e] = ppf[order[e]];
+    c.pp_pose[e] = c.node_idx[F.nodes[0]];
+    c.pp_plane[e] = c.node_idx[F.nodes[1]];
+    std::memcpy(&c.pp_meas[(size_t)e * 4], F.meas, 4 * sizeof(double));
+    std::memcpy(&c.pp_sinf[(size_t)e * 6], F.sinf, 6 * sizeof(double));
+    c.pp_ptr[c.pp_pose[e] + 1]++;
+  }
+  for (int p = 0; p < N; p++) c.pp_ptr[p + 1] += c.pp_ptr[p];
+  c.ntile = (E + kTile - 1) / kTile;
+  const int slots = c.ntile * kTile;
+  // partial slots for the pose-major sweep: one per (tile, pose) run
+  c.pm_part.assign(slots, -1);
+  c.ypart_ptr.assign(N + 1, 0);
+  {
+    int np = 0;
+    for (int e = 0; e < E; e++) {
+      bool head = (e % kTile == 0) || (c.pp_pose[e] != c.pp_pose[e - 1]);
+      if (head) { np++; c.ypart_ptr[c.pp_pose[e] + 1]++; }
+      c.pm_part[e] = np - 1;
+    }
+    c.n_ypart = np;
+    for (int p = 0; p < N; p++) c.ypart_ptr[p + 1] += c.ypart_ptr[p];
+    // partial ids are assigned in edge order == pose order, so pose p owns [ypart_ptr[p], ypart_ptr[p+1])
+  }
+  // ---- plane-major view ----
+  std::vector<int> pord(E);
+  for (int i = 0; i < E; i++) pord[i] = i;
+  std::stable_sort(pord.begin(), pord.end(), [&](int a, int b) { return c.pp_plane[a] < c.pp_plane[b]; });
+  c.pl2pm.assign(slots, -1); c.pl_plane.assign(slots, -1); c.pl_pose.assign(slots, 0); c.pl_part.assign(slots, -1);
+  c.pm2pl.assign(E, -1);
+  c.pl_ptr.assign(M + 1, 0); c.upart_ptr.assign(M + 1, 0);
+  {
+    int np = 0;
+    for (int s = 0; s < E; s++) {
+      int e = pord[s];
+      c.pl2pm[s] = e; c.pm2pl[e] = s;
+      c.pl_plane[s] = c.pp_plane[e]; c.pl_pose[s] = c.pp_pose[e];
+      c.pl_ptr[c.pp_plane[e] + 1]++;
+      bool head = (s % kTile == 0) || (c.pl_plane[s] != c.pl_plane[s - 1]);
+      if (head) { np++; c.upart_ptr[c.pl_plane[s] + 1]++; }
+      c.pl_part[s] = np - 1;
+    }
+    c.n_upart = np;
+    for (int l = 0; l < M; l++) { c.pl_ptr[l + 1] += c.pl_ptr[l]; c.upart_ptr[l + 1] += c.upart_ptr[l]; }
+  }
+  // ---- incidence lists ----
+  c.pinc_ptr.assign(N + 1, 0);
+  for (int f = 0; f < c.Epf; f++) { c.pinc_ptr[c.pf_i[f] + 1]++; if (c.pf_j[f] >= 0) c.pinc_ptr[c.pf_j[f] + 1]++; }
+  for (int p = 0; p < N; p++) c.pinc_ptr[p + 1] += c.pinc_ptr[p];
+  c.pinc.assign(c.pinc_ptr[N], 0);
+  {
+    std::vector<int> fill(c.pinc_ptr.begin(), c.pinc_ptr.end() - 1);
+    for (int f = 0; f < c.Epf; f++) {
+      c.pinc[fill[c.pf_i[f]]++] = (f << 1) | 0;
+      if (c.pf_j[f] >= 0) c.pinc[fill[c.pf_j[f]]++] = (f << 1) | 1;
+    }
+  }
+  c.linc_ptr.assign(M + 1, 0);
+  for (int f = 0; f < c.Elp; f++) c.linc_ptr[c.lp_plane[f] + 1]++;
+  for (int l = 0; l < M; l++) c.linc_ptr[l + 1] += c.linc_ptr[l];
+  c.linc.assign(c.linc_ptr[M], 0);
+  {
+    std::vector<int> fill(c.linc_ptr.begin(), c.linc_ptr.end() - 1);
+    for (int f = 0; f < c.Elp; f++) c.linc[fill[c.lp_plane[f]]++] = f;
+  }
+  // ---- dense-block groups ----
+  c.nblk = (N + kBlockPoses - 1) / kBlockPoses;
+  c.blk_grp_ptr.assign(c.nblk + 1, 0);
+  c.grp_mem.resize(E);
+  for (int k = 0; k < c.nblk; k++) {
+    int p0 = k * kBlockPoses, p1 = std::min(N, p0 + kBlockPoses);
+    int e0 = c.pp_ptr[p0], e1 = c.pp_ptr[p1];
+    std::vector<int> es(e1 - e0);
+    for (int e = e0; e < e1; e++) es[e - e0] = e;
+    std::stable_sort(es.begin(), es.end(), [&](int a, int b) { return c.pp_plane[a] < c.pp_plane[b]; });
+    for (int i = 0; i < (int)es.size(); i++) {
+      if (i == 0 || c.pp_plane[es[i]] != c.pp_plane[es[i - 1]]) {
+        c.grp_plane.push_back(c.pp_plane[es[i]]);
+        c.grp_mem_ptr.push_back(e0 + i);
+      }
+      c.grp_mem[e0 + i] = es[i];
+    }
+    c.blk_grp_ptr[k + 1] = (int)c.grp_plane.size();
+  }
+  c.grp_mem_ptr.push_back(E);
+  c.ngrp = (int)c.grp_plane.size();
+  // ---- coarse (plane, node) pairs ----
+  c.nc = coarse_nodes(N);
+  c.ce_ptr.assign(M + 1, 0);
+  for (int l = 0; l < M; l++) {
+    int s0 = c.pl_ptr[l], s1 = c.pl_ptr[l + 1];
+    int last = -1;
+    for (int s = s0; s < s1; s++) {
+      int p = c.pl_pose[s];
+      int c0 = p / kCoarseSpacing;
+      int cand[2] = {c0, (p % kCoarseSpacing) ? c0 + 1 : -1};
+      for (int q = 0; q < 2; q++) {
+        int nd = cand[q];
+        if (nd < 0 || nd <= last) continue;
+        // slots of plane l supporting node nd: poses in ((nd-1)*SP, (nd+1)*SP)
+        int lo = s, hi = s;
+        // lo: first slot with pose > (nd-1)*SP ; since slots are pose-sorted within the plane, scan
+        lo = s0;
+        while (lo < s1 && c.pl_pose[lo] <= (nd - 1) * kCoarseSpacing) lo++;
+        hi = lo;
+        while (hi < s1 && c.pl_pose[hi] < (nd + 1) * kCoarseSpacing) hi++;
+        c.ce_node.push_back(nd); c.ce_plane.push_back(l); c.ce_lo.push_back(lo); c.ce_hi.push_back(hi);
+        last = nd;
+      }
+    }
+    c.ce_ptr[l + 1] = (int)c.ce_node.size();
+  }
+  c.nce = (int)c.ce_node.size();
+  c.n2ce_ptr.assign(c.nc + 1, 0);
+  for (int i = 0; i < c.nce; i++) c.n2ce_ptr[c.ce_node[i] + 1]++;
+  for (int a = 0; a < c.nc; a++) c.n2ce_ptr[a + 1] += c.n2ce_ptr[a];
+  c.n2ce.assign(c.nce, 0);
+  {
+    std::vector<int> fill(c.n2ce_ptr.begin(), c.n2ce_ptr.end() - 1);
+    for (int i = 0; i < c.nce; i++) c.n2ce[fill[c.ce_node[i]]++] = i;
+  }
+  return true;
+}
+
+}  // namespace pus

@@ -1,0 +1,999 @@
+// pus_kernels.cuh -- the device-resident Levenberg-Marquardt / Gauss-Newton loop for pose-plane
+// factor graphs, written for sm_100a (B200): one persistent kernel, one CTA per SM, the CTAs of a
+// "team" cooperate on one graph through a global-memory barrier (teams of one CTA for batches of
+// small graphs).  Per LM trial step:
+//   linearise   every residual + closed-form 3x6 / 3x3 (6x6) Jacobian blocks in one sweep, W = Jp^T Jl
+//               written in both pose-major and plane-major warp tiles ([tile][18][32] doubles)
+//   assemble    Hpp, gp (per pose), Hll, gl (per plane) by fixed-order gathers (no float atomics)
+//   Schur       Hll^-1 (3x3), dense 96x96 diagonal blocks of S = Hpp - W Hll^-1 W^T inverted in shared
+//               memory, Galerkin coarse operator on piecewise-linear trajectory modes inverted in HBM
+//   PCG         implicit-Schur operator: plane-major sweep (W^T p), plane solve, pose-major sweep (W v),
+//               two-level additive preconditioner, deterministic segmented reductions
+//   update      exmap of every vertex, trial chi2, accept / reject, lambda rule -- all on device
+// Control flow follows Optimizer::levenberg_marquardt / gauss_newton / relinearize of the reference
+// (pop_planar_slam/Thirdparty/isam/isamlib/Optimizer.cpp:371-467, 286-366, 114-185).
+#pragma once
+#include <cuda_runtime.h>
+
+#include "pus_graph.hpp"
+
+namespace pus {
+
+constexpr int kThreads = 512;
+constexpr int kWarps = kThreads / 32;
+constexpr int kSlots = 5;  // pose blocks handled concurrently by one CTA (5 x 96 = 480 threads)
+constexpr int kTraceCap = 1024;
+constexpr int kMaxStage = 64;  // staged group members in the dense-block build
+
+enum KernelMode { MODE_BATCH = 0, MODE_UPDATE = 1, MODE_DEBUG = 2, MODE_CHI2 = 3 };
+
+struct LmParams {
+  int method;  // 0 GN, 1 LM
+  double eps2, eps_abs, eps_rel;
+  int max_iter;
+  double lambda0, lambda_factor;
+  int robust_kind;
+  double robust_b;
+  double pcg_tol;
+  int pcg_max_iter;
+  int mode;
+  int debug_stage;
+  double debug_lambda;
+  int restore_init;
+};
+
+struct LmResult {
+  int iterations, accepted, relin, chi2_evals;
+  long long pcg_iters;
+  double chi2_initial, chi2_final;
+  int trace_n, status;
+  unsigned long long phase_ns[8];
+};
+
+struct LmTrace {
+  double lambda[kTraceCap], chi2_new[kTraceCap], chi2_before[kTraceCap], delta_norm[kTraceCap];
+  int accepted[kTraceCap], pcg[kTraceCap];
+};
+
+struct DevGraph {
+  int N, M, Epl, Epf, Elp, ntile, nblk, nc, SP, n_upart, n_ypart, nce, ngrp;
+  // vertex values
+  double *pose_lin, *pose_trial, *pose_init, *plane_lin, *plane_trial, *plane_init;
+  // pose-plane edges (pose-major) and plane-major view
+  const int *pp_pose, *pp_plane, *pp_ptr, *pm2pl, *pm_part, *ypart_ptr;
+  const double *pp_meas, *pp_sinf;
+  const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr;
+  // pose factors / plane priors
+  const int *pf_i, *pf_j, *pinc_ptr, *pinc;
+  const double *pf_meas, *pf_sinf;
+  const int *lp_plane, *linc_ptr, *linc;
+  const double *lp_meas, *lp_sinf;
+  // dense-block groups, coarse pairs
+  const int *blk_grp_ptr, *grp_plane, *grp_mem_ptr, *grp_mem;
+  const int *ce_ptr, *ce_node, *ce_plane, *ce_lo, *ce_hi, *n2ce_ptr, *n2ce;
+  // work buffers
+  double *W, *Wt, *JP, *JL, *PF, *LP;
+  double *Hpp, *gp, *Hll, *gl, *Hinv, *vl, *dl;
+  double *upart, *ypart;
+  double *Binv, *Wc, *Ac[2];
+  double *x, *r, *z, *q, *b, *pv[2];
+  double *rcpart[2], *qcpart;
+  double *red;
+  LmParams prm;
+  LmResult* res;
+  LmTrace* trace;
+};
+
+// ---------------------------------------------------------------------------------------------
+struct Ctx {
+  int rank, tsize;       // CTA rank within its team, CTAs per team
+  unsigned* bar;         // team barrier counter (zeroed by the host before launch)
+  unsigned bar_target;   // thread 0 only
+  int red_slot;
+  unsigned char* smem;   // dynamic shared memory
+};
+
+__device__ __forceinline__ double ldc(const double* p) { return __ldcg(p); }
+__device__ __forceinline__ int ldc(const int* p) { return __ldcg(p); }
+
+__device__ __forceinline__ unsigned long long gtime() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs of the team must call this the same number of times.
+__device__ __forceinline__ void team_barrier(Ctx& c) {
+  __syncthreads();
+  if (c.tsize > 1) {
+    if (threadIdx.x == 0) {
+      c.bar_target += (unsigned)c.tsize;
+      __threadfence();
+      atomicAdd(c.bar, 1u);
+      while (ld_acquire_u32(c.bar) < c.bar_target) { }
+      __threadfence();
+    }
+    __syncthreads();
+  }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int d = 16; d > 0; d >>= 1) v += __shfl_xor_sync(0xffffffffu, v, d);
+  return v;
+}
+
+// shared-memory carve-up (bytes)
+constexpr int kSmRed = 0;                            // [kWarps][4] + [4] doubles
+constexpr int kSmRedBytes = (kWarps * 4 + 8) * 8;
+constexpr int kSmWork = 1024;                        // start of the phase-specific area
+// dense-block build: S0, S1 (96x96), Wg, Yg (kMaxStage x 18), P (36), Hinv (9)
+constexpr int kSmS0 = kSmWork;
+constexpr int kSmS1 = kSmS0 + kBlockDim * kBlockDim * 8;
+constexpr int kSmWg = kSmS1 + kBlockDim * kBlockDim * 8;
+constexpr int kSmYg = kSmWg + kMaxStage * 18 * 8;
+constexpr int kSmP = kSmYg + kMaxStage * 18 * 8;
+constexpr int kSmHi = kSmP + 36 * 8;
+constexpr int kSmBuildEnd = kSmHi + 16 * 8;
+// PCG phases: sA, sB [kSlots*96], szc [kSlots][12][8], rc [6*nc]
+constexpr int kSmA = kSmWork;
+constexpr int kSmB = kSmA + kSlots * kBlockDim * 8;
+constexpr int kSmZc = kSmB + kSlots * kBlockDim * 8;
+constexpr int kSmRc = kSmZc + kSlots * 12 * 8 * 8;
+constexpr int kSmemBytes = kSmBuildEnd;              // >= kSmRc + 6*nc*8 is checked on the host
+
+// deterministic team-wide sum of K (<= 4) values; result broadcast to every thread
+template <int K>
+__device__ __forceinline__ void team_reduce(Ctx& c, double* red, double* v) {
+  double* s = reinterpret_cast<double*>(c.smem + kSmRed);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < K; k++) v[k] = warp_sum(v[k]);
+  __syncthreads();  // protect s from a previous use
+  if (lane == 0)
+    for (int k = 0; k < K; k++) s[warp * 4 + k] = v[k];
+  __syncthreads();
+  if (threadIdx.x < K) {
+    double acc = 0;
+    for (int w = 0; w < kWarps; w++) acc += s[w * 4 + threadIdx.x];
+    if (c.tsize > 1) red[((size_t)c.red_slot * c.tsize + c.rank) * 4 + threadIdx.x] = acc;
+    else s[kWarps * 4 + threadIdx.x] = acc;
+  }
+  if (c.tsize > 1) {
+    team_barrier(c);
+    if (threadIdx.x < K) {
+      double acc = 0;
+      for (int r = 0; r < c.tsize; r++) acc += ldc(red + ((size_t)c.red_slot * c.tsize + r) * 4 + threadIdx.x);
+      s[kWarps * 4 + threadIdx.x] = acc;
+    }
+    c.red_slot = (c.red_slot + 1) & 3;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < K; k++) v[k] = s[kWarps * 4 + k];
+}
+
+// segmented (by sorted key) suffix sums inside a warp: afterwards the first lane of every run of equal
+// keys holds the run's total, accumulated in a fixed order
+template <int K>
+__device__ __forceinline__ void seg_suffix_sum(int key, double* v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int d = 1; d < 32; d <<= 1) {
+    int ok = __shfl_down_sync(0xffffffffu, key, d);
+    bool take = (lane + d < 32) && (ok == key);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double o = __shfl_down_sync(0xffffffffu, v[k], d);
+      if (take) v[k] += o;
+    }
+  }
+}
+
+// inverse of a 6x6 (symmetric positive definite in exact arithmetic) matrix by Gauss-Jordan, row-major
+__device__ __forceinline__ void inv6(const double* A, double* Ai) {
+  double a[36];
+  for (int i = 0; i < 36; i++) a[i] = A[i];
+  for (int k = 0; k < 6; k++) {
+    double piv = 1.0 / a[k * 6 + k];
+    for (int j = 0; j < 6; j++) a[k * 6 + j] = (j == k) ? piv : a[k * 6 + j] * piv;
+    for (int i = 0; i < 6; i++) {
+      if (i == k) continue;
+      double f = a[i * 6 + k];
+      for (int j = 0; j < 6; j++) a[i * 6 + j] = (j == k) ? -f * piv : a[i * 6 + j] - f * a[k * 6 + j];
+    }
+  }
+  for (int i = 0; i < 36; i++) Ai[i] = a[i];
+}
+
+// one pivot step of the blocked Gauss-Jordan inversion for the 6x6 block (i,j):
+//   (k,k): P ; (k,j): P A_kj ; (i,k): -A_ik P ; else A_ij - A_ik P A_kj      (P = A_kk^-1)
+template <typename Load>
+__device__ __forceinline__ void gj_block(Load ld, double* dst, int ldm, int i, int j, int k, const double* P) {
+  double out[36];
+  if (i == k && j == k) {
+    for (int e = 0; e < 36; e++) out[e] = P[e];
+  } else if (i == k) {
+    double B[36];
+    for (int e = 0; e < 36; e++) B[e] = ld((k * 6 + e / 6) * ldm + j * 6 + e % 6);
+    for (int r = 0; r < 6; r++)
+      for (int cc = 0; cc < 6; cc++) {
+        double s = 0;
+        for (int t = 0; t < 6; t++) s += P[r * 6 + t] * B[t * 6 + cc];
+        out[r * 6 + cc] = s;
+      }
+  } else {
+    double A[36], T[36];
+    for (int e = 0; e < 36; e++) A[e] = ld((i * 6 + e / 6) * ldm + k * 6 + e % 6);
+    for (int r = 0; r < 6; r++)
+      for (int cc = 0; cc < 6; cc++) {
+        double s = 0;
+        for (int t = 0; t < 6; t++) s += A[r * 6 + t] * P[t * 6 + cc];
+        T[r * 6 + cc] = s;
+      }
+    if (j == k) {
+      for (int e = 0; e < 36; e++) out[e] = -T[e];
+    } else {
+      for (int e = 0; e < 36; e++) A[e] = ld((k * 6 + e / 6) * ldm + j * 6 + e % 6);
+      for (int r = 0; r < 6; r++)
+        for (int cc = 0; cc < 6; cc++) {
+          double s = ld((i * 6 + r) * ldm + j * 6 + cc);
+          for (int t = 0; t < 6; t++) s -= T[r * 6 + t] * A[t * 6 + cc];
+          out[r * 6 + cc] = s;
+        }
+    }
+  }
+  for (int e = 0; e < 36; e++) dst[(i * 6 + e / 6) * ldm + j * 6 + e % 6] = out[e];
+}
+
+// ---------------------------------------------------------------------------------------------
+// phases
+// ---------------------------------------------------------------------------------------------
+struct Phase {
+  const DevGraph& G;
+  Ctx& c;
+  __device__ Phase(const DevGraph& g, Ctx& cc) : G(g), c(cc) {}
+
+  __device__ __forceinline__ int tid_team() const { return c.rank * kThreads + threadIdx.x; }
+  __device__ __forceinline__ int nthr_team() const { return c.tsize * kThreads; }
+  __device__ __forceinline__ int warp_team() const { return c.rank * kWarps + (threadIdx.x >> 5); }
+  __device__ __forceinline__ int nwarp_team() const { return c.tsize * kWarps; }
+
+  // -------- restore the uploaded initial estimate (repeatable resident solves) --------
+  __device__ void restore_init() {
+    for (int i = tid_team(); i < G.N * 7; i += nthr_team()) G.pose_lin[i] = G.pose_init[i];
+    for (int i = tid_team(); i < G.M * 4; i += nthr_team()) G.plane_lin[i] = G.plane_init[i];
+  }
+
+  // -------- linearise: pose-plane edges --------
+  __device__ void lin_pose_plane() {
+    const int lane = threadIdx.x & 31;
+    for (int tile = warp_team(); tile < G.ntile; tile += nwarp_team()) {
+      int e = tile * 32 + lane;
+      if (e < G.Epl) {
+        int p = G.pp_pose[e], l = G.pp_plane[e];
+        double pose[7], pl[4], m[4], si[6];
+        for (int i = 0; i < 7; i++) pose[i] = ldc(G.pose_lin + (size_t)p * 7 + i);
+        for (int i = 0; i < 4; i++) pl[i] = ldc(G.plane_lin + (size_t)l * 4 + i);
+        for (int i = 0; i < 4; i++) m[i] = G.pp_meas[(size_t)e * 4 + i];
+        for (int i = 0; i < 6; i++) si[i] = G.pp_sinf[(size_t)e * 6 + i];
+        double r[3], Jp[18], Jl[9];
+        pose_plane_linearize(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, Jp, Jl);
+        double* w = G.W + (size_t)tile * kWStride + lane;
+        int s = G.pm2pl[e];
+        double* wt = G.Wt + (size_t)(s >> 5) * kWStride + (s & 31);
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) {
+            double v = Jp[a] * Jl[b] + Jp[6 + a] * Jl[3 + b] + Jp[12 + a] * Jl[6 + b];
+            w[(a * 3 + b) * 32] = v;
+            wt[(a * 3 + b) * 32] = v;
+          }
+        double* jp = G.JP + (size_t)e * 21;
+        for (int i = 0; i < 18; i++) jp[i] = Jp[i];
+        jp[18] = r[0]; jp[19] = r[1]; jp[20] = r[2];
+        double* jl = G.JL + (size_t)e * 12;
+        for (int i = 0; i < 9; i++) jl[i] = Jl[i];
+        jl[9] = r[0]; jl[10] = r[1]; jl[11] = r[2];
+      }
+    }
+  }
+
+  // -------- linearise: pose priors / odometry, plane priors --------
+  __device__ void lin_other() {
+    for (int f = tid_team(); f < G.Epf; f += nthr_team()) {
+      int i = G.pf_i[f], j = G.pf_j[f];
+      double p1[7], p2[7], m[6], si[21];
+      for (int t = 0; t < 7; t++) p1[t] = ldc(G.pose_lin + (size_t)i * 7 + t);
+      if (j >= 0) for (int t = 0; t < 7; t++) p2[t] = ldc(G.pose_lin + (size_t)j * 7 + t);
+      for (int t = 0; t < 6; t++) m[t] = G.pf_meas[(size_t)f * 6 + t];
+      for (int t = 0; t < 21; t++) si[t] = G.pf_sinf[(size_t)f * 21 + t];
+      double r[6], J1[36], J2[36];
+      for (int t = 0; t < 36; t++) J2[t] = 0;
+      pose_factor_linearize(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
+      double* o = G.PF + (size_t)f * 120;
+      for (int a = 0; a < 6; a++)
+        for (int b = 0; b < 6; b++) {
+          double s11 = 0, s22 = 0, s12 = 0;
+          for (int k = 0; k < 6; k++) {
+            s11 += J1[k * 6 + a] * J1[k * 6 + b];
+            s22 += J2[k * 6 + a] * J2[k * 6 + b];
+            s12 += J1[k * 6 + a] * J2[k * 6 + b];
+          }
+          o[a * 6 + b] = s11; o[36 + a * 6 + b] = s22; o[72 + a * 6 + b] = s12;
+        }
+      for (int a = 0; a < 6; a++) {
+        double b1 = 0, b2 = 0;
+        for (int k = 0; k < 6; k++) { b1 += J1[k * 6 + a] * r[k]; b2 += J2[k * 6 + a] * r[k]; }
+        o[108 + a] = b1; o[114 + a] = b2;
+      }
+    }
+    for (int f = tid_team(); f < G.Elp; f += nthr_team()) {
+      int l = G.lp_plane[f];
+      double pl[4], m[4], si[6];
+      for (int t = 0; t < 4; t++) pl[t] = ldc(G.plane_lin + (size_t)l * 4 + t);
+      for (int t = 0; t < 4; t++) m[t] = G.lp_meas[(size_t)f * 4 + t];
+      for (int t = 0; t < 6; t++) si[t] = G.lp_sinf[(size_t)f * 6 + t];
+      double r[3], Jl[9];
+      pose_plane_linearize(nullptr, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, Jl);
+      double* o = G.LP + (size_t)f * 12;
+      for (int a = 0; a < 3; a++) {
+        for (int b = 0; b < 3; b++) o[a * 3 + b] = Jl[a] * Jl[b] + Jl[3 + a] * Jl[3 + b] + Jl[6 + a] * Jl[6 + b];
+        o[9 + a] = Jl[a] * r[0] + Jl[3 + a] * r[1] + Jl[6 + a] * r[2];
+      }
+    }
+  }
+
+  // -------- assemble Hpp / gp (thread per (pose, entry)) and Hll / gl (warp per plane) --------
+  __device__ void assemble() {
+    const long long total = (long long)G.N * 42;
+    for (long long idx = tid_team(); idx < total; idx += nthr_team()) {
+      int p = (int)(idx / 42), en = (int)(idx % 42);
+      int e0 = G.pp_ptr[p], e1 = G.pp_ptr[p + 1];
+      int i0 = G.pinc_ptr[p], i1 = G.pinc_ptr[p + 1];
+      double acc = 0;
+      if (en < 36) {
+        int a = en / 6, b = en % 6;
+        for (int e = e0; e < e1; e++) {
+          const double* jp = G.JP + (size_t)e * 21;
+          acc += ldc(jp + a) * ldc(jp + b) + ldc(jp + 6 + a) * ldc(jp + 6 + b) + ldc(jp + 12 + a) * ldc(jp + 12 + b);
+        }
+        for (int k = i0; k < i1; k++) {
+          int inc = G.pinc[k];
+          acc += ldc(G.PF + (size_t)(inc >> 1) * 120 + (inc & 1) * 36 + en);
+        }
+        G.Hpp[(size_t)p * 36 + en] = acc;
+      } else {
+        int a = en - 36;
+        for (int e = e0; e < e1; e++) {
+          const double* jp = G.JP + (size_t)e * 21;
+          acc += ldc(jp + a) * ldc(jp + 18) + ldc(jp + 6 + a) * ldc(jp + 19) + ldc(jp + 12 + a) * ldc(jp + 20);
+        }
+        for (int k = i0; k < i1; k++) {
+          int inc = G.pinc[k];
+          acc += ldc(G.PF + (size_t)(inc >> 1) * 120 + 108 + (inc & 1) * 6 + a);
+        }
+        G.gp[(size_t)p * 6 + a] = acc;
+      }
+    }
+    const int lane = threadIdx.x & 31;
+    for (int l = warp_team(); l < G.M; l += nwarp_team()) {
+      double h[9];
+      for (int k = 0; k < 9; k++) h[k] = 0;  // 0..5: Hll upper (00,01,02,11,12,22); 6..8: gl
+      for (int s = G.pl_ptr[l] + lane; s < G.pl_ptr[l + 1]; s += 32) {
+        const double* jl = G.JL + (size_t)G.pl2pm[s] * 12;
+        double J[12];
+        for (int k = 0; k < 12; k++) J[k] = ldc(jl + k);
+        h[0] += J[0] * J[0] + J[3] * J[3] + J[6] * J[6];
+        h[1] += J[0] * J[1] + J[3] * J[4] + J[6] * J[7];
+        h[2] += J[0] * J[2] + J[3] * J[5] + J[6] * J[8];
+        h[3] += J[1] * J[1] + J[4] * J[4] + J[7] * J[7];
+        h[4] += J[1] * J[2] + J[4] * J[5] + J[7] * J[8];
+        h[5] += J[2] * J[2] + J[5] * J[5] + J[8] * J[8];
+        h[6] += J[0] * J[9] + J[3] * J[10] + J[6] * J[11];
+        h[7] += J[1] * J[9] + J[4] * J[10] + J[7] * J[11];
+        h[8] += J[2] * J[9] + J[5] * J[10] + J[8] * J[11];
+      }
+      for (int k = 0; k < 9; k++) h[k] = warp_sum(h[k]);
+      if (lane == 0) {
+        double H[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
+        double gg[3] = {h[6], h[7], h[8]};
+        for (int k = G.linc_ptr[l]; k < G.linc_ptr[l + 1]; k++) {
+          const double* o = G.LP + (size_t)G.linc[k] * 12;
+          for (int t = 0; t < 9; t++) H[t] += ldc(o + t);
+          for (int t = 0; t < 3; t++) gg[t] += ldc(o + 9 + t);
+        }
+        for (int t = 0; t < 9; t++) G.Hll[(size_t)l * 9 + t] = H[t];
+        for (int t = 0; t < 3; t++) G.gl[(size_t)l * 3 + t] = gg[t];
+      }
+    }
+  }
+
+  // -------- chi2 at the linearisation point (trial = false) or the trial values --------
+  __device__ double chi2(bool trial) {
+    const double* PV = trial ? G.pose_trial : G.pose_lin;
+    const double* LV = trial ? G.plane_trial : G.plane_lin;
+    double acc = 0;
+    for (int e = tid_team(); e < G.Epl; e += nthr_team()) {
+      int p = G.pp_pose[e], l = G.pp_plane[e];
+      double pose[7], pl[4], m[4], si[6], r[3];
+      for (int i = 0; i < 7; i++) pose[i] = ldc(PV + (size_t)p * 7 + i);
+      for (int i = 0; i < 4; i++) pl[i] = ldc(LV + (size_t)l * 4 + i);
+      for (int i = 0; i < 4; i++) m[i] = G.pp_meas[(size_t)e * 4 + i];
+      for (int i = 0; i < 6; i++) si[i] = G.pp_sinf[(size_t)e * 6 + i];
+      pose_plane_linearize(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, nullptr);
+      acc += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    }
+    for (int f = tid_team(); f < G.Epf; f += nthr_team()) {
+      int i = G.pf_i[f], j = G.pf_j[f];
+      double p1[7], p2[7], m[6], si[21], r[6];
+      for (int t = 0; t < 7; t++) p1[t] = ldc(PV + (size_t)i * 7 + t);
+      if (j >= 0) for (int t = 0; t < 7; t++) p2[t] = ldc(PV + (size_t)j * 7 + t);
+      for (int t = 0; t < 6; t++) m[t] = G.pf_meas[(size_t)f * 6 + t];
+      for (int t = 0; t < 21; t++) si[t] = G.pf_sinf[(size_t)f * 21 + t];
+      pose_factor_linearize(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, nullptr);
+      for (int t = 0; t < 6; t++) acc += r[t] * r[t];
+    }
+    for (int f = tid_team(); f < G.Elp; f += nthr_team()) {
+      int l = G.lp_plane[f];
+      double pl[4], m[4], si[6], r[3];
+      for (int t = 0; t < 4; t++) pl[t] = ldc(LV + (size_t)l * 4 + t);
+      for (int t = 0; t < 4; t++) m[t] = G.lp_meas[(size_t)f * 4 + t];
+      for (int t = 0; t < 6; t++) si[t] = G.lp_sinf[(size_t)f * 6 + t];
+      pose_plane_linearize(nullptr, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, nullptr);
+      acc += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
+    }
+    double v[1] = {acc};
+    team_reduce<1>(c, G.red, v);
+    return v[0];
+  }
+
+  // -------- Schur setup, part 1: damped Hll^-1 and vl = Hll^-1 gl --------
+  __device__ void plane_inverse(double lambda) {
+    for (int l = tid_team(); l < G.M; l += nthr_team()) {
+      double H[9], Hi[9];
+      for (int t = 0; t < 9; t++) H[t] = ldc(G.Hll + (size_t)l * 9 + t);
+      H[0] *= (1 + lambda); H[4] *= (1 + lambda); H[8] *= (1 + lambda);  // Cholesky.cpp:91-97
+      sym3_inverse(H, Hi);
+      for (int t = 0; t < 9; t++) G.Hinv[(size_t)l * 9 + t] = Hi[t];
+      double g0 = ldc(G.gl + (size_t)l * 3), g1 = ldc(G.gl + (size_t)l * 3 + 1), g2 = ldc(G.gl + (size_t)l * 3 + 2);
+      for (int t = 0; t < 3; t++) G.vl[(size_t)l * 3 + t] = Hi[t * 3] * g0 + Hi[t * 3 + 1] * g1 + Hi[t * 3 + 2] * g2;
+    }
+  }
+
+  // -------- Schur setup, part 2: dense diagonal blocks of S, inverted in shared memory --------
+  __device__ void build_blocks(double lambda) {
+    double* S0 = reinterpret_cast<double*>(c.smem + kSmS0);
+    double* S1 = reinterpret_cast<double*>(c.smem + kSmS1);
+    double* Wg = reinterpret_cast<double*>(c.smem + kSmWg);
+    double* Yg = reinterpret_cast<double*>(c.smem + kSmYg);
+    double* Ps = reinterpret_cast<double*>(c.smem + kSmP);
+    double* His = reinterpret_cast<double*>(c.smem + kSmHi);
+    const int tid = threadIdx.x;
+    for (int k = c.rank; k < G.nblk; k += c.tsize) {
+      const int p0 = k * kBlockPoses;
+      const int np = min(kBlockPoses, G.N - p0);
+      __syncthreads();
+      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) S0[i] = 0.0;
+      __syncthreads();
+      // diagonal 6x6 blocks (damped) and identity padding
+      for (int i = tid; i < kBlockPoses * 36; i += kThreads) {
+        int pi = i / 36, en = i % 36, a = en / 6, b = en % 6;
+        double v;
+        if (pi < np) {
+          v = ldc(G.Hpp + (size_t)(p0 + pi) * 36 + en);
+          if (a == b) v *= (1 + lambda);
+        } else {
+          v = (a == b) ? 1.0 : 0.0;
+        }
+        S0[(pi * 6 + a) * kBlockDim + pi * 6 + b] = v;
+      }
+      __syncthreads();
+      // pose-pose factors with both ends inside the block (handled from side 0)
+      for (int pi = 0; pi < np; pi++) {
+        int i0 = G.pinc_ptr[p0 + pi], i1 = G.pinc_ptr[p0 + pi + 1];
+        for (int kk = i0; kk < i1; kk++) {
+          int inc = G.pinc[kk];
+          if (inc & 1) continue;
+          int f = inc >> 1, j = G.pf_j[f];
+          if (j < p0 || j >= p0 + np || j == p0 + pi) continue;
+          int pj = j - p0;
+          if (tid < 36) {
+            int a = tid / 6, b = tid % 6;
+            double v = ldc(G.PF + (size_t)f * 120 + 72 + tid);
+            S0[(pi * 6 + a) * kBlockDim + pj * 6 + b] += v;
+            S0[(pj * 6 + b) * kBlockDim + pi * 6 + a] += v;
+          }
+          __syncthreads();
+        }
+      }
+      // minus W Hll^-1 W^T restricted to the block, one plane group at a time
+      for (int g = G.blk_grp_ptr[k]; g < G.blk_grp_ptr[k + 1]; g++) {
+        const int m0 = G.grp_mem_ptr[g], m = G.grp_mem_ptr[g + 1] - m0;
+        const int l = G.grp_plane[g];
+        __syncthreads();
+        if (tid < 9) His[tid] = ldc(G.Hinv + (size_t)l * 9 + tid);
+        const bool staged = (m <= kMaxStage);
+        if (staged) {
+          for (int i = tid; i < m * 18; i += kThreads) {
+            int mi = i / 18, kk = i % 18;
+            int e = G.grp_mem[m0 + mi];
+            Wg[i] = ldc(G.W + (size_t)(e >> 5) * kWStride + kk * 32 + (e & 31));
+          }
+        }
+        __syncthreads();
+        if (staged) {
+          for (int i = tid; i < m * 18; i += kThreads) {
+            int mi = i / 18, kk = i % 18, a = kk / 3, b = kk % 3;
+            Yg[i] = Wg[mi * 18 + a * 3] * His[0 * 3 + b] + Wg[mi * 18 + a * 3 + 1] * His[1 * 3 + b] + Wg[mi * 18 + a * 3 + 2] * His[2 * 3 + b];
+          }
+        }
+        __syncthreads();
+        const int total = m * m * 36;
+        for (int idx = tid; idx < total; idx += kThreads) {
+          int mi = idx / (36 * m), rem = idx % (36 * m);
+          int mj = rem / 36, en = rem % 36, a = en / 6, b = en % 6;
+          int ei = G.grp_mem[m0 + mi], ej = G.grp_mem[m0 + mj];
+          int pi = G.pp_pose[ei] - p0, pj = G.pp_pose[ej] - p0;
+          double v;
+          if (staged) {
+            v = Yg[mi * 18 + a * 3] * Wg[mj * 18 + b * 3] + Yg[mi * 18 + a * 3 + 1] * Wg[mj * 18 + b * 3 + 1] +
+                Yg[mi * 18 + a * 3 + 2] * Wg[mj * 18 + b * 3 + 2];
+          } else {
+            double wi[3], wj[3];
+            for (int t = 0; t < 3; t++) {
+              wi[t] = ldc(G.W + (size_t)(ei >> 5) * kWStride + (a * 3 + t) * 32 + (ei & 31));
+              wj[t] = ldc(G.W + (size_t)(ej >> 5) * kWStride + (b * 3 + t) * 32 + (ej & 31));
+            }
+            v = 0;
+            for (int t = 0; t < 3; t++) {
+              double y = wi[0] * His[0 * 3 + t] + wi[1] * His[1 * 3 + t] + wi[2] * His[2 * 3 + t];
+              v += y * wj[t];
+            }
+          }
+          // distinct (mi,mj) pairs of one group hit distinct entries unless a pose observes the
+          // plane twice; the atomic keeps that (rare) case correct
+          atomicAdd(&S0[(pi * 6 + a) * kBlockDim + pj * 6 + b], -v);
+        }
+      }
+      __syncthreads();
+      // blocked Gauss-Jordan inversion in shared memory (ping-pong S0 <-> S1)
+      double* src = S0;
+      double* dst = S1;
+      for (int kk = 0; kk < kBlockPoses; kk++) {
+        if (tid == 0) {
+          double A[36], Pi[36];
+          for (int e = 0; e < 36; e++) A[e] = src[(kk * 6 + e / 6) * kBlockDim + kk * 6 + e % 6];
+          inv6(A, Pi);
+          for (int e = 0; e < 36; e++) Ps[e] = Pi[e];
+        }
+        __syncthreads();
+        if (tid < kBlockPoses * kBlockPoses) {
+          double P[36];
+          for (int e = 0; e < 36; e++) P[e] = Ps[e];
+          const double* s = src;
+          gj_block([s](int off) { return s[off]; }, dst, kBlockDim, tid / kBlockPoses, tid % kBlockPoses, kk, P);
+        }
+        __syncthreads();
+        double* t = src; src = dst; dst = t;
+      }
+      double* out = G.Binv + (size_t)k * kBlockDim * kBlockDim;
+      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) out[i] = src[i];
+    }
+    __syncthreads();
+  }
+
+  __device__ __forceinline__ double hat(int p, int node) const {
+    int d = p - node * G.SP;
+    if (d < 0) d = -d;
+    return d >= G.SP ? 0.0 : 1.0 - (double)d / (double)G.SP;
+  }
+
+  // -------- Schur setup, part 3: coarse pairs Wc = P^T W (warp per (plane, node) pair) --------
+  __device__ void coarse_wc() {
+    const int lane = threadIdx.x & 31;
+    for (int ce = warp_team(); ce < G.nce; ce += nwarp_team()) {
+      int node = G.ce_node[ce];
+      double acc[18];
+      for (int k = 0; k < 18; k++) acc[k] = 0;
+      for (int s = G.ce_lo[ce] + lane; s < G.ce_hi[ce]; s += 32) {
+        double w = hat(G.pl_pose[s], node);
+        const double* wt = G.Wt + (size_t)(s >> 5) * kWStride + (s & 31);
+        for (int k = 0; k < 18; k++) acc[k] += w * ldc(wt + k * 32);
+      }
+      for (int k = 0; k < 18; k++) acc[k] = warp_sum(acc[k]);
+      if (lane < 18) {
+        double v = acc[0];
+#pragma unroll
+        for (int k = 1; k < 18; k++) if (lane == k) v = acc[k];
+        G.Wc[(size_t)ce * 18 + lane] = v;
+      }
+    }
+  }
+
+  // -------- Schur setup, part 4: A_c = P^T S P, one warp per coarse row panel --------
+  __device__ void coarse_assemble(double lambda) {
+    const int lane = threadIdx.x & 31;
+    const int ldm = 6 * G.nc;
+    double* A = G.Ac[0];
+    for (int a = warp_team(); a < G.nc; a += nwarp_team()) {
+      for (int i = lane; i < 6 * ldm; i += 32) A[(size_t)a * 6 * ldm + i] = 0.0;
+      __syncwarp();
+      // P^T Hpp_d P and pose-pose off-diagonals
+      int plo = max(0, (a - 1) * G.SP + 1), phi = min(G.N, (a + 1) * G.SP);
+      for (int p = plo; p < phi; p++) {
+        double ha = hat(p, a);
+        int c0 = p / G.SP;
+        for (int q = 0; q < 2; q++) {
+          int bnode = c0 + q;
+          if (bnode >= G.nc) continue;
+          double hb = hat(p, bnode);
+          if (hb == 0.0) continue;
+          for (int en = lane; en < 36; en += 32) {
+            int r = en / 6, cc = en % 6;
+            double v = ldc(G.Hpp + (size_t)p * 36 + en);
+            if (r == cc) v *= (1 + lambda);
+            { double* dstp = &A[((size_t)a * 6 + r) * ldm + bnode * 6 + cc]; *dstp = ldc(dstp) + (ha * hb * v); }
+          }
+        }
+        for (int kk = G.pinc_ptr[p]; kk < G.pinc_ptr[p + 1]; kk++) {
+          int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
+          int j = G.pf_j[f];
+          if (j < 0) continue;
+          int o = side ? G.pf_i[f] : j;  // the other pose
+          int oc0 = o / G.SP;
+          for (int q = 0; q < 2; q++) {
+            int bnode = oc0 + q;
+            if (bnode >= G.nc) continue;
+            double hb = hat(o, bnode);
+            if (hb == 0.0) continue;
+            for (int en = lane; en < 36; en += 32) {
+              int r = en / 6, cc = en % 6;
+              // block (p, o) of Hpp: A12 if p is side 0, A12^T otherwise
+              double v = side ? ldc(G.PF + (size_t)f * 120 + 72 + cc * 6 + r) : ldc(G.PF + (size_t)f * 120 + 72 + en);
+              { double* dstp = &A[((size_t)a * 6 + r) * ldm + bnode * 6 + cc]; *dstp = ldc(dstp) + (ha * hb * v); }
+            }
+          }
+        }
+      }
+      __syncwarp();
+      // minus sum over planes touching node a:  Wc[a,l] Hinv_l Wc[b,l]^T
+      for (int t = G.n2ce_ptr[a]; t < G.n2ce_ptr[a + 1]; t++) {
+        int cea = G.n2ce[t];
+        int l = G.ce_plane[cea];
+        double Y[18];  // Wc[a,l] * Hinv  (6x3)
+        {
+          double Wa[18], Hi[9];
+          for (int k = 0; k < 18; k++) Wa[k] = ldc(G.Wc + (size_t)cea * 18 + k);
+          for (int k = 0; k < 9; k++) Hi[k] = ldc(G.Hinv + (size_t)l * 9 + k);
+          for (int r = 0; r < 6; r++)
+            for (int b = 0; b < 3; b++) Y[r * 3 + b] = Wa[r * 3] * Hi[b] + Wa[r * 3 + 1] * Hi[3 + b] + Wa[r * 3 + 2] * Hi[6 + b];
+        }
+        for (int ceb = G.ce_ptr[l]; ceb < G.ce_ptr[l + 1]; ceb++) {
+          int bnode = G.ce_node[ceb];
+          for (int en = lane; en < 36; en += 32) {
+            int r = en / 6, cc = en % 6;
+            const double* wb = G.Wc + (size_t)ceb * 18 + cc * 3;
+            double v = Y[r * 3] * ldc(wb) + Y[r * 3 + 1] * ldc(wb + 1) + Y[r * 3 + 2] * ldc(wb + 2);
+            { double* dstp = &A[((size_t)a * 6 + r) * ldm + bnode * 6 + cc]; *dstp = ldc(dstp) - (v); }
+          }
+        }
+      }
+    }
+  }
+
+  // -------- Schur setup, part 5: invert A_c in HBM (blocked Gauss-Jordan, one team barrier per pivot) ---
+  // returns the index of the buffer holding A_c^-1
+  __device__ int coarse_invert() {
+    const int nc = G.nc, ldm = 6 * nc;
+    double* Ps = reinterpret_cast<double*>(c.smem + kSmP);
+    int cur = 0;
+    for (int kk = 0; kk < nc; kk++) {
+      const double* src = G.Ac[cur];
+      double* dst = G.Ac[cur ^ 1];
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        double A[36], Pi[36];
+        for (int e = 0; e < 36; e++) A[e] = ldc(src + (size_t)(kk * 6 + e / 6) * ldm + kk * 6 + e % 6);
+        inv6(A, Pi);
+        for (int e = 0; e < 36; e++) Ps[e] = Pi[e];
+      }
+      __syncthreads();
+      double P[36];
+      for (int e = 0; e < 36; e++) P[e] = Ps[e];
+      const long long nb2 = (long long)nc * nc;
+      for (long long b = tid_team(); b < nb2; b += nthr_team())
+        gj_block([src](int off) { return ldc(src + off); }, dst, ldm, (int)(b / nc), (int)(b % nc), kk, P);
+      team_barrier(c);
+      cur ^= 1;
+    }
+    return cur;
+  }
+
+  // -------- plane-major sweep: upart = segmented sums of Wt^T * (va + beta*vb)[pose] --------
+  __device__ void sweep_planes(const double* va, const double* vb, double beta) {
+    const int lane = threadIdx.x & 31;
+    for (int tile = warp_team(); tile < G.ntile; tile += nwarp_team()) {
+      int s = tile * 32 + lane;
+      int key = G.pl_plane[s];
+      double u[3] = {0, 0, 0};
+      if (key >= 0) {
+        int p = G.pl_pose[s];
+        double x[6];
+        for (int a = 0; a < 6; a++) x[a] = ldc(va + (size_t)p * 6 + a);
+        if (vb) for (int a = 0; a < 6; a++) x[a] += beta * ldc(vb + (size_t)p * 6 + a);
+        const double* wt = G.Wt + (size_t)tile * kWStride + lane;
+#pragma unroll
+        for (int a = 0; a < 6; a++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) u[b] += ldc(wt + (a * 3 + b) * 32) * x[a];
+      }
+      seg_suffix_sum<3>(key, u);
+      int pk = __shfl_up_sync(0xffffffffu, key, 1);
+      if (key >= 0 && (lane == 0 || pk != key)) {
+        double* o = G.upart + (size_t)G.pl_part[s] * 3;
+        o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+      }
+    }
+  }
+
+  // -------- plane solve: mode 0: vl = Hinv * sum(upart) ; mode 1: dl = Hinv * (-gl - sum(upart)), returns |dl|^2
+  __device__ double solve_planes(int mode) {
+    const int lane = threadIdx.x & 31;
+    double nrm = 0;
+    for (int l = warp_team(); l < G.M; l += nwarp_team()) {
+      double u[3] = {0, 0, 0};
+      for (int k = G.upart_ptr[l] + lane; k < G.upart_ptr[l + 1]; k += 32)
+        for (int b = 0; b < 3; b++) u[b] += ldc(G.upart + (size_t)k * 3 + b);
+      for (int b = 0; b < 3; b++) u[b] = warp_sum(u[b]);
+      if (lane == 0) {
+        double Hi[9];
+        for (int t = 0; t < 9; t++) Hi[t] = ldc(G.Hinv + (size_t)l * 9 + t);
+        if (mode == 1) for (int b = 0; b < 3; b++) u[b] = -ldc(G.gl + (size_t)l * 3 + b) - u[b];
+        double* o = (mode == 0 ? G.vl : G.dl) + (size_t)l * 3;
+        for (int t = 0; t < 3; t++) {
+          double v = Hi[t * 3] * u[0] + Hi[t * 3 + 1] * u[1] + Hi[t * 3 + 2] * u[2];
+          o[t] = v;
+          nrm += v * v;
+        }
+      }
+    }
+    return nrm;
+  }
+
+  // -------- pose-major sweep: ypart = segmented sums of W * vl[plane] --------
+  __device__ void sweep_poses() {
+    const int lane = threadIdx.x & 31;
+    for (int tile = warp_team(); tile < G.ntile; tile += nwarp_team()) {
+      int e = tile * 32 + lane;
+      int key = (e < G.Epl) ? G.pp_pose[e] : -1;
+      double y[6] = {0, 0, 0, 0, 0, 0};
+      if (key >= 0) {
+        int l = G.pp_plane[e];
+        double v0 = ldc(G.vl + (size_t)l * 3), v1 = ldc(G.vl + (size_t)l * 3 + 1), v2 = ldc(G.vl + (size_t)l * 3 + 2);
+        const double* w = G.W + (size_t)tile * kWStride + lane;
+#pragma unroll
+        for (int a = 0; a < 6; a++) y[a] = ldc(w + (a * 3) * 32) * v0 + ldc(w + (a * 3 + 1) * 32) * v1 + ldc(w + (a * 3 + 2) * 32) * v2;
+      }
+      seg_suffix_sum<6>(key, y);
+      int pk = __shfl_up_sync(0xffffffffu, key, 1);
+      if (key >= 0 && (lane == 0 || pk != key)) {
+        double* o = G.ypart + (size_t)G.pm_part[e] * 6;
+        for (int a = 0; a < 6; a++) o[a] = y[a];
+      }
+    }
+  }
+
+  // number of rounds every CTA of the team runs over its owned pose blocks
+  __device__ __forceinline__ int rounds() const { return (G.nblk + c.tsize * kSlots - 1) / (c.tsize * kSlots); }
+
+  // coarse restriction of the per-slot vector in `sv` (smem [kSlots][96]); writes 12 values per block
+  __device__ __forceinline__ void restrict_block(const double* sv, int slot, int u, int k, int np, double* out) {
+    if (u < 12 && k < G.nblk) {
+      int node = u / 6, row = u % 6;
+      int p0 = k * kBlockPoses, c0 = p0 / G.SP;
+      double acc = 0;
+      for (int pi = 0; pi < np; pi++) acc += hat(p0 + pi, c0 + node) * sv[slot * kBlockDim + pi * 6 + row];
+      out[(size_t)k * 12 + u] = acc;
+    }
+  }
+
+  // -------- right-hand side: b = -gp + sum(ypart) ; x = 0 ; r = b ; p = 0 ; rcpart[0] = P^T b --------
+  __device__ void make_rhs() {
+    double* sA = reinterpret_cast<double*>(c.smem + kSmA);
+    const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
+    for (int rd = 0; rd < rounds(); rd++) {
+      int k = c.rank + c.tsize * (slot + kSlots * rd);
+      int p = k * kBlockPoses + u / 6, row = u % 6;
+      bool live = (slot < kSlots) && (k < G.nblk);
+      int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
+      bool on = live && (p < G.N);
+      __syncthreads();
+      if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
+      if (on) {
+        double v = -ldc(G.gp + (size_t)p * 6 + row);
+        for (int t = G.ypart_ptr[p]; t < G.ypart_ptr[p + 1]; t++) v += ldc(G.ypart + (size_t)t * 6 + row);
+        size_t o = (size_t)p * 6 + row;
+        G.b[o] = v; G.r[o] = v; G.x[o] = 0.0; G.pv[0][o] = 0.0; G.pv[1][o] = 0.0; G.z[o] = 0.0; G.q[o] = 0.0;
+        sA[slot * kBlockDim + u] = v;
+      }
+      __syncthreads();
+      if (live) restrict_block(sA, slot, u, k, np, G.rcpart[0]);
+    }
+  }
+
+  // -------- PCG: owner part of the direction update p_new = z + beta p_old --------
+  __device__ void update_direction(int cur, double beta) {
+    const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
+    for (int rd = 0; rd < rounds(); rd++) {
+      int k = c.rank + c.tsize * (slot + kSlots * rd);
+      int p = k * kBlockPoses + u / 6;
+      if (slot < kSlots && k < G.nblk && p < G.N) {
+        size_t o = (size_t)p * 6 + u % 6;
+        G.pv[cur ^ 1][o] = ldc(G.z + o) + beta * ldc(G.pv[cur] + o);
+      }
+    }
+  }
+
+  // -------- PCG: q = S p for owned poses (given ypart), qcpart = P^T q, returns partial p.q --------
+  __device__ double apply_pose_side(const double* pvec, double lambda, double* qout, double* qc) {
+    double* sA = reinterpret_cast<double*>(c.smem + kSmA);
+    const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
+    double dot = 0;
+    for (int rd = 0; rd < rounds(); rd++) {
+      int k = c.rank + c.tsize * (slot + kSlots * rd);
+      int p = k * kBlockPoses + u / 6, row = u % 6;
+      bool live = (slot < kSlots) && (k < G.nblk);
+      int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
+      bool on = live && (p < G.N);
+      __syncthreads();
+      if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
+      if (on) {
+        const double* H = G.Hpp + (size_t)p * 36 + row * 6;
+        double pr = 0, v = 0;
+        for (int cc = 0; cc < 6; cc++) {
+          double pc = ldc(pvec + (size_t)p * 6 + cc);
+          double h = ldc(H + cc);
+          if (cc == row) { pr = pc; h *= (1 + lambda); }
+          v += h * pc;
+        }
+        for (int kk = G.pinc_ptr[p]; kk < G.pinc_ptr[p + 1]; kk++) {
+          int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
+          int j = G.pf_j[f];
+          if (j < 0) continue;
+          int o = side ? G.pf_i[f] : j;
+          const double* A12 = G.PF + (size_t)f * 120 + 72;
+          for (int cc = 0; cc < 6; cc++) {
+            double a = side ? ldc(A12 + cc * 6 + row) : ldc(A12 + row * 6 + cc);
+            v += a * ldc(pvec + (size_t)o * 6 + cc);
+          }
+        }
+        for (int t = G.ypart_ptr[p]; t < G.ypart_ptr[p + 1]; t++) v -= ldc(G.ypart + (size_t)t * 6 + row);
+        qout[(size_t)p * 6 + row] = v;
+        sA[slot * kBlockDim + u] = v;
+        dot += pr * v;
+      }
+      __syncthreads();
+      if (live && qc) restrict_block(sA, slot, u, k, np, qc);
+    }
+    return dot;
+  }
+
+  // -------- PCG: x += alpha p ; r -= alpha q ; z = M^-1 r (dense block + coarse) ; returns partial r.z ----
+  // rc_old / rc_new: ping-pong buffers of per-block coarse restrictions of r
+  __device__ double precondition(double alpha, const double* pvec, int acinv, const double* rc_old, double* rc_new,
+                                 bool first) {
+    double* sA = reinterpret_cast<double*>(c.smem + kSmA);   // r_new per slot
+    double* szc = reinterpret_cast<double*>(c.smem + kSmZc); // [kSlots][12][8]
+    double* src = reinterpret_cast<double*>(c.smem + kSmRc); // coarse residual, 6*nc
+    const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
+    const int ldm = 6 * G.nc;
+    const int bpn = G.SP / kBlockPoses;  // blocks per coarse interval
+    // full coarse residual rc = sum_k rc_old[k] - alpha * sum_k qcpart[k]  (linear in r)
+    __syncthreads();
+    for (int i = tid; i < ldm; i += kThreads) {
+      int node = i / 6, row = i % 6;
+      double acc = 0;
+      for (int side = 0; side < 2; side++) {
+        int cint = node - side;  // interval whose blocks have c0 == cint; they feed `node` through slot `side`
+        if (cint < 0) continue;
+        int k0 = cint * bpn, k1 = min(G.nblk, k0 + bpn);
+        for (int k = k0; k < k1; k++) {
+          double v = ldc(rc_old + (size_t)k * 12 + side * 6 + row);
+          if (!first) v -= alpha * ldc(G.qcpart + (size_t)k * 12 + side * 6 + row);
+          acc += v;
+        }
+      }
+      src[i] = acc;
+    }
+    __syncthreads();
+    const double* Ai = G.Ac[acinv];
+    double dot = 0;
+    for (int rd = 0; rd < rounds(); rd++) {
+      int k = c.rank + c.tsize * (slot + kSlots * rd);
+      int p = k * kBlockPoses + u / 6, row = u % 6;
+      bool live = (slot < kSlots) && (k < G.nblk);
+      int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
+      bool on = live && (p < G.N);
+      __syncthreads();
+      double rn = 0;
+      if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
+      if (on) {
+        size_t o = (size_t)p * 6 + row;
+        rn = ldc(G.r + o);
+        if (!first) {
+          double pp = ldc(pvec + o);
+          rn -= alpha * ldc(G.q + o);
+          G.x[o] = ldc(G.x + o) + alpha * pp;
+          G.r[o] = rn;
+        }
+        sA[slot * kBlockDim + u] = rn;
+      }
+      // coarse part: rows of A_c^-1 for the two nodes bracketing the block
+      if (live) {
+        int c0 = (k * kBlockPoses) / G.SP;
+        int oidx = u / 8, part = u % 8;  // 12 outputs x 8 partial sums
+        int node = c0 + oidx / 6;
+        double acc = 0;
+        if (node < G.nc) {
+          const double* arow = Ai + (size_t)(node * 6 + oidx % 6) * ldm;
+          for (int j = part; j < ldm; j += 8) acc += ldc(arow + j) * src[j];
+        }
+        szc[(slot * 12 + oidx) * 8 + part] = acc;
+      }
+      __syncthreads();
+      if (live) restrict_block(sA, slot, u, k, np, rc_new);
+      if (on) {
+        // dense block: z_local = Binv[k] r_block (symmetric: read column u)
+        const double* B = G.Binv + (size_t)k * kBlockDim * kBlockDim + u;
+        double zl = 0;
+        for (int j = 0; j < kBlockDim; j++) zl += ldc(B + (size_t)j * kBlockDim) * sA[slot * kBlockDim + j];
+        int c0 = (k * kBlockPoses) / G.SP;
+        double z0 = 0, z1 = 0;
+        for (int t = 0; t < 8; t++) { z0 += szc[(slot * 12 + row) * 8 + t]; z1 += szc[(slot * 12 + 6 + row) * 8 + t]; }
+        double zz = zl + hat(p, c0) * z0 + hat(p, c0 + 1) * z1;
+        G.z[(size_t)p * 6 + row] = zz;
+        dot += rn * zz;
+      }
+    }
+    return dot;
+  }
+
+  // -------- |x|^2 over owned poses --------
+  __device__ double norm_x() {
+    double acc = 0;
+    for (int i = tid_team(); i < G.N * 6; i += nthr_team()) { double v = ldc(G.x + i); acc += v * v; }
+    return acc;
+  }
+
+  // -------- trial = lin (+) delta --------
+  __device__ void apply_delta() {
+    for (int p = tid_team(); p < G.N; p += nthr_team()) {
+      double v[7], d[6], o[7];
+      for (int i = 0; i < 7; i++) v[i] = ldc(G.pose_lin + (size_t)p * 7 + i);
+      for (int i = 0; i < 6; i++) d[i] = ldc(G.x + (size_t)p * 6 + i);
+      pose_exmap(v, d, o);
+      for (int i = 0; i < 7; i++) G.pose_trial[(size_t)p * 7 + i] = o[i];
+    }
+    for (int l = tid_team(); l < G.M; l += nthr_team()) {
+      double v[4], d[3], o[4];
+      for (int i = 0; i < 4; i++) v[i] = ldc(G.plane_lin + (size_t)l * 4 + i);
+      for (int i = 0; i < 3; i++) d[i] = ldc(G.dl + (size_t)l * 3 + i);
+      plane_exmap(v, d, o);
+      for (int i = 0; i < 4; i++) G.plane_trial[(size_t)l * 4 + i] = o[i];
+    }
+  }
+  __device__ void accept_trial() {
+    for (int i = tid_team(); i < G.N * 7; i += nthr_team()) G.pose_lin[i] = ldc(G.pose_trial + i);
+    for (int i = tid_team(); i < G.M * 4; i += nthr_team()) G.plane_lin[i] = ldc(G.plane_trial + i);
+  }
+};
+
+}  // namespace pus
