@@ -206,6 +206,13 @@ inline Pose pose_from_mat4(const double m[16]) {
   p.t[0] = T[3]; p.t[1] = T[7]; p.t[2] = T[11];
   double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
   p.q = wRo_to_quat(R);
+  // DEVIATION from the reference (the only one in this file): renormalise.  Upstream keeps the raw
+  // Eigen::Quaterniond(Matrix3d); the matrix->quaternion->matrix cycle of oplus() amplifies the error of
+  // |q|^2 by ~tan^2(theta/2) per cycle, so dead-reckoning a few hundred poses at camera-like attitudes
+  // reaches |q| = 1.01 and the Euler residuals stop being functions of a rotation.  Within the reference's
+  // own regime (80 key-frames) both versions agree to rounding.
+  double nq = std::sqrt(p.q.w * p.q.w + p.q.x * p.q.x + p.q.y * p.q.y + p.q.z * p.q.z);
+  p.q.w /= nq; p.q.x /= nq; p.q.y /= nq; p.q.z /= nq;
   return p;
 }
 

@@ -175,6 +175,13 @@ PUS_HD void T_to_pose(const double* m, double* p) {  // Pose3d(Matrix4d) Pose3d.
   p[0] = T[3]; p[1] = T[7]; p[2] = T[11];
   double R[9] = {T[0], T[1], T[2], T[4], T[5], T[6], T[8], T[9], T[10]};
   R_to_quat(R, p + 3);
+  // Deviation from the reference (documented in DESIGN.md): the matrix -> quaternion -> matrix cycle of
+  // Pose3d::oplus is not norm-preserving in floating point (the error of |q|^2 is amplified by about
+  // tan^2(theta/2) per cycle), so a dead-reckoned chain of a few hundred poses at camera-like attitudes
+  // (theta > 90 deg) drifts to |q| = 1.01.  Renormalising changes a unit quaternion only at rounding level.
+  double* q = p + 3;
+  double nq = sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+  q[0] /= nq; q[1] /= nq; q[2] /= nq; q[3] /= nq;
 }
 PUS_HD void mat4_mul(const double* A, const double* B, double* C) {
   for (int i = 0; i < 4; i++)

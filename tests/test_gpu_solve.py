@@ -21,9 +21,10 @@ def compare(gpu, orc, ig, io, tol=TOL):
     assert np.abs(P_g[:, :3] - P_o[:, :3]).max() <= tol * scale
     sq = np.sign(np.sum(P_g[:, 3:] * P_o[:, 3:], axis=1))[:, None]
     assert np.abs(P_g[:, 3:] * sq - P_o[:, 3:]).max() <= tol
-    L_g, L_o = gpu.get_planes(ig["plane_ids"]), orc.get_planes(io["plane_ids"])
-    sl = np.sign(np.sum(L_g * L_o, axis=1))[:, None]
-    assert np.abs(L_g * sl - L_o).max() <= tol
+    if len(ig["plane_ids"]):
+        L_g, L_o = gpu.get_planes(ig["plane_ids"]), orc.get_planes(io["plane_ids"])
+        sl = np.sign(np.sum(L_g * L_o, axis=1))[:, None]
+        assert np.abs(L_g * sl - L_o).max() <= tol
 
 
 @pytest.mark.parametrize("cfg,seed,jac", [(1, 0, 0), (1, 1, 1), (2, 0, 0), (2, 3, 1)])
