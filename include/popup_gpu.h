@@ -96,6 +96,9 @@ int pus_add_planes(pus_handle h, int n, const double* abcds, int* out_ids);
 /* NodeT::init  Node.h:123-126 (Mapping.cpp:475, 499) */
 int pus_init_pose(pus_handle h, int id, const double* init7);
 int pus_init_plane(pus_handle h, int id, const double* abcd);
+/* bulk NodeT::init over n vertices (values packed like the single-vertex forms) */
+int pus_init_poses(pus_handle h, int n, const int* ids, const double* init7s);
+int pus_init_planes(pus_handle h, int n, const int* ids, const double* abcds);
 /* NodeT::value()  Node.h:130 */
 int pus_get_pose(pus_handle h, int id, double* out7);
 int pus_get_plane(pus_handle h, int id, double* out4);

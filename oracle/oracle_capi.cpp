@@ -64,6 +64,14 @@ int orc_init_plane(void* h, int id, const double* v) {
   if (!valid_node(S(h), id, NODE_PLANE)) { g_err = "bad plane id"; return -1; }
   S(h)->init_plane(id, plane_from_vec4(v)); return 0;
 }
+int orc_init_poses(void* h, int n, const int* ids, const double* v) {
+  for (int i = 0; i < n; i++) if (orc_init_pose(h, ids[i], v + 7 * i) < 0) return -1;
+  return 0;
+}
+int orc_init_planes(void* h, int n, const int* ids, const double* v) {
+  for (int i = 0; i < n; i++) if (orc_init_plane(h, ids[i], v + 4 * i) < 0) return -1;
+  return 0;
+}
 int orc_get_pose(void* h, int id, double* out7) {
   if (!valid_node(S(h), id, NODE_POSE)) { g_err = "bad pose id"; return -1; }
   pose_to7(S(h)->nodes[id].pose, out7); return 0;

@@ -150,6 +150,14 @@ class GraphAPI:
     def init_plane(self, id_, abcd):
         self._chk(self._f("init_plane")(self.h, int(id_), _dp(_f64(abcd, (4,)))))
 
+    def init_poses(self, ids, init7s):
+        ids, v = _i32(ids), _f64(init7s, (len(ids), 7))
+        self._chk(self._f("init_poses")(self.h, len(ids), _ip(ids), _dp(v)))
+
+    def init_planes(self, ids, abcds):
+        ids, v = _i32(ids), _f64(abcds, (len(ids), 4))
+        self._chk(self._f("init_planes")(self.h, len(ids), _ip(ids), _dp(v)))
+
     def get_pose(self, id_):
         out = np.empty(7)
         self._chk(self._f("get_pose")(self.h, int(id_), _dp(out)))

@@ -642,6 +642,14 @@ int pus_init_plane(pus_handle h, int id, const double* v) {
   if (!SV(h)->g.ok_node(id, NODE_PLANE)) { g_err = "bad plane id"; return -1; }
   SV(h)->g.init_node(id, v); return 0;
 }
+int pus_init_poses(pus_handle h, int n, const int* ids, const double* v) {
+  for (int i = 0; i < n; i++) if (pus_init_pose(h, ids[i], v + 7 * i) < 0) return -1;
+  return 0;
+}
+int pus_init_planes(pus_handle h, int n, const int* ids, const double* v) {
+  for (int i = 0; i < n; i++) if (pus_init_plane(h, ids[i], v + 4 * i) < 0) return -1;
+  return 0;
+}
 int pus_get_pose(pus_handle h, int id, double* out) {
   NEED(h);
   if (!SV(h)->g.ok_node(id, NODE_POSE)) { g_err = "bad pose id"; return -1; }
