@@ -73,7 +73,9 @@ typedef struct pus_stats {
   int n_poses, n_planes, n_pose_plane, n_odometry, n_pose_prior, n_plane_prior;
   int gpu_launches;       /* kernels launched by the last call */
   int grid_ctas, block_threads;
-  double phase_ms[8];     /* in-kernel %globaltimer split: 0 linearise,1 schur/precond,2 pcg,3 backsub+update,4 chi2 */
+  double phase_ms[24];    /* in-kernel %globaltimer split: 0 linearise, 1 Schur set-up, 2 PCG, 3 back-substitution + update,
+                             4 chi2; 8..12 set-up parts (Hll^-1, dense blocks, Wc, A_c, A_c^-1); 16..20 PCG parts
+                             (plane sweep, plane solve, pose sweep, pose side + dot, preconditioner + dot) */
 } pus_stats;
 
 /* ---- lifetime ------------------------------------------------------------------------- */

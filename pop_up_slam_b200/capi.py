@@ -38,7 +38,7 @@ class Stats(C.Structure):
                 ("d2h_ms", C.c_double), ("h2d_bytes", C.c_longlong), ("d2h_bytes", C.c_longlong),
                 ("n_poses", C.c_int), ("n_planes", C.c_int), ("n_pose_plane", C.c_int), ("n_odometry", C.c_int),
                 ("n_pose_prior", C.c_int), ("n_plane_prior", C.c_int), ("gpu_launches", C.c_int),
-                ("grid_ctas", C.c_int), ("block_threads", C.c_int), ("phase_ms", C.c_double * 8)]
+                ("grid_ctas", C.c_int), ("block_threads", C.c_int), ("phase_ms", C.c_double * 24)]
 
     def as_dict(self):
         d = {}

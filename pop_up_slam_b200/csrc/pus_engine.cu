@@ -17,20 +17,6 @@ namespace pus {
 // ---------------------------------------------------------------------------------------------
 // device: LM / GN driver
 // ---------------------------------------------------------------------------------------------
-struct Timer {
-  bool on;
-  unsigned long long t0;
-  LmResult* res;
-  __device__ Timer(bool o, LmResult* r) : on(o), t0(0), res(r) { if (on) t0 = gtime(); }
-  __device__ void lap(int slot) {
-    if (on) {
-      unsigned long long t = gtime();
-      res->phase_ns[slot] += t - t0;
-      t0 = t;
-    }
-  }
-};
-
 __device__ void linearize(Phase& ph, Ctx& c) {
   ph.lin_pose_plane();
   ph.lin_other();
@@ -40,23 +26,35 @@ __device__ void linearize(Phase& ph, Ctx& c) {
 }
 
 // Schur complement set-up for a damping value; returns the buffer index of A_c^-1
-__device__ int schur_setup(Phase& ph, Ctx& c, double lambda) {
+// Schur complement set-up for a damping value.  Hll^-1 (part of the operator) is always rebuilt; the two-level
+// preconditioner (dense diagonal blocks + coarse Galerkin inverse) only when `rebuild` -- a stale
+// preconditioner changes the PCG iteration count, never the solution.  Returns the buffer index of A_c^-1.
+__device__ int schur_setup(Phase& ph, Ctx& c, double lambda, Timer& ft, bool rebuild, int acinv_prev) {
+  ft.sync();
   ph.plane_inverse(lambda);
   team_barrier(c);
+  ft.lap(8);
+  if (!rebuild) return acinv_prev;
   ph.build_blocks(lambda);
+  ft.lap(9);
   ph.coarse_wc();
   team_barrier(c);
+  ft.lap(10);
   ph.coarse_assemble(lambda);
   team_barrier(c);
-  return ph.coarse_invert();
+  ft.lap(11);
+  int r = ph.coarse_invert();
+  ft.lap(12);
+  return r;
 }
 
 // Solve (Hpp_d - W Hll_d^-1 W^T) x = -gp + W Hll_d^-1 gl by preconditioned CG, then back-substitute the
 // planes.  Returns |delta|; *its = PCG iterations.
-__device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambda, int acinv, int* its) {
-  ph.sweep_poses();  // with vl = Hll^-1 gl (plane_inverse)
-  team_barrier(c);
-  ph.make_rhs();
+// `warm`: start from the previous solution (kept in G.xprev) -- used after a rejected LM step, where only lambda changed.
+__device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambda, int acinv, int* its, Timer& ft, bool warm) {
+  ph.cache_blocks();
+  c.smem_cache_ok = 1;
+  ph.pose_phase(true, nullptr, lambda, nullptr, nullptr);  // rhs, with vl = Hll^-1 gl from plane_inverse
   team_barrier(c);
   double v[2];
   int rcb = 0, cur = 0, it = 0;
@@ -66,22 +64,35 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
   const double rz0 = v[0];
   double rz = rz0, beta = 0.0;
   const double tol2 = G.prm.pcg_tol * G.prm.pcg_tol;
-  if (rz0 > 0.0) {
+  bool done = false;
+  if (warm && rz0 > 0.0) {
+    // one pseudo-iteration with direction p = x_prev and step 1:  x = x_prev, r = b - S x_prev, z = M^-1 r
+    ph.sweep_planes(G.xprev, nullptr, 0.0);
+    team_barrier(c);
+    ph.pose_phase(false, G.xprev, lambda, G.q, G.qcpart);
+    team_barrier(c);
+    v[0] = ph.precondition(1.0, G.xprev, acinv, G.rcpart[rcb], G.rcpart[rcb ^ 1], false);
+    team_reduce<1>(c, G.red, v);
+    rcb ^= 1;
+    rz = v[0];
+    if (!(rz > tol2 * rz0)) done = true;
+  }
+  if (rz0 > 0.0 && !done) {
     while (it < G.prm.pcg_max_iter) {
+      ft.sync();
       ph.update_direction(cur, beta);
-      ph.sweep_planes(G.z, G.pv[cur], beta);
+      ph.sweep_planes(G.z, G.pv[cur], beta, G.zc);
       team_barrier(c);
-      ph.solve_planes(0);
-      team_barrier(c);
-      ph.sweep_poses();
-      team_barrier(c);
-      v[0] = ph.apply_pose_side(G.pv[cur ^ 1], lambda, G.q, G.qcpart);
+      ft.lap(16);
+      v[0] = ph.pose_phase(false, G.pv[cur ^ 1], lambda, G.q, G.qcpart);
       team_reduce<1>(c, G.red, v);
+      ft.lap(19);
       const double pq = v[0];
       if (!(pq > 0.0)) break;  // breakdown (not SPD / exhausted precision)
       const double alpha = rz / pq;
       v[0] = ph.precondition(alpha, G.pv[cur ^ 1], acinv, G.rcpart[rcb], G.rcpart[rcb ^ 1], false);
       team_reduce<1>(c, G.red, v);
+      ft.lap(20);
       rcb ^= 1;
       it++;
       const double rz_new = v[0];
@@ -95,7 +106,7 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
   // planes: dl = Hll_d^-1 (-gl - W^T x)
   ph.sweep_planes(G.x, nullptr, 0.0);
   team_barrier(c);
-  v[0] = ph.solve_planes(1) + ph.norm_x();
+  v[0] = ph.solve_planes(1) + ph.norm_x();  // (also keeps a copy of x for the next warm start)
   team_reduce<1>(c, G.red, v);
   return sqrt(v[0]);
 }
@@ -105,11 +116,13 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
   const LmParams& P = G.prm;
   const bool lead = (c.rank == 0 && threadIdx.x == 0);
   LmResult* res = G.res;
-  Timer tm(lead, res);
+  Timer tm(lead, c.smem);
+  Timer& ft = tm;
+  ph.ft = (P.fine_timers ? &tm : nullptr);
   if (lead) {
     res->iterations = 0; res->accepted = 0; res->relin = 0; res->chi2_evals = 0; res->pcg_iters = 0;
     res->trace_n = 0; res->status = 0; res->chi2_initial = 0; res->chi2_final = 0;
-    for (int i = 0; i < 8; i++) res->phase_ns[i] = 0;
+    for (int i = 0; i < 24; i++) res->phase_ns[i] = 0;
   }
   if (P.restore_init) { ph.restore_init(); team_barrier(c); }
   if (P.mode == MODE_CHI2) {
@@ -121,22 +134,18 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
     if (P.debug_stage == 3) {  // q = S * pv[0] with the current linearisation / Schur set-up
       ph.sweep_planes(G.pv[0], nullptr, 0.0);
       team_barrier(c);
-      ph.solve_planes(0);
-      team_barrier(c);
-      ph.sweep_poses();
-      team_barrier(c);
-      ph.apply_pose_side(G.pv[0], P.debug_lambda, G.q, nullptr);
+      ph.pose_phase(false, G.pv[0], P.debug_lambda, G.q, nullptr);
       team_barrier(c);
       return;
     }
     linearize(ph, c);
     if (lead) res->relin = 1;
     if (P.debug_stage >= 1) {
-      int acinv = schur_setup(ph, c, P.debug_lambda);
+      int acinv = schur_setup(ph, c, P.debug_lambda, ft, true, 0);
       if (lead) res->status = acinv;
       if (P.debug_stage >= 2) {
         int its = 0;
-        double dn = schur_solve(ph, c, G, P.debug_lambda, acinv, &its);
+        double dn = schur_solve(ph, c, G, P.debug_lambda, acinv, &its, ft, false);
         if (lead) { res->pcg_iters = its; res->chi2_final = dn; }
       }
     }
@@ -154,10 +163,12 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
   if (P.mode == MODE_BATCH) { err = ph.chi2(false); nchi++; }
   tm.lap(4);
   const double err0 = err;
-  int acinv = schur_setup(ph, c, lambda);
+  int acinv = schur_setup(ph, c, lambda, ft, true, 0);
+  int prec_builds = 1;
   tm.lap(1);
-  double dnorm = schur_solve(ph, c, G, lambda, acinv, &its);
+  double dnorm = schur_solve(ph, c, G, lambda, acinv, &its, ft, false);
   pcg_total += its;
+  int its_ref = its;  // PCG iterations right after the last preconditioner build
   tm.lap(2);
   if (P.mode == MODE_UPDATE) {
     // Optimizer::relinearize (GN branch): estimate = linpoint (+) h_gn
@@ -183,6 +194,7 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
         t->lambda[iter - 1] = lambda; t->chi2_new[iter - 1] = err_new; t->chi2_before[iter - 1] = err;
         t->delta_norm[iter - 1] = dnorm; t->accepted[iter - 1] = diff > 0.0 ? 1 : 0; t->pcg[iter - 1] = last_pcg;
       }
+      const bool rejected = !(diff > 0.0);
       if (diff > 0.0) {
         accepted++;
         ph.accept_trial();
@@ -202,9 +214,15 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
         lambda *= P.lambda_factor;
       }
       if (stop) break;
-      acinv = schur_setup(ph, c, lambda);
-      tm.lap(1);
-      dnorm = schur_solve(ph, c, G, lambda, acinv, &its);
+      {
+        // refresh the preconditioner only when the last solve needed clearly more iterations than the one right
+        // after the previous build (deterministic rule, identical on every CTA)
+        const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref + its_ref / 2 + 8);
+        acinv = schur_setup(ph, c, lambda, ft, rebuild, acinv);
+        tm.lap(1);
+        dnorm = schur_solve(ph, c, G, lambda, acinv, &its, ft, rejected && P.warm_start);
+        if (rebuild) { its_ref = its; prec_builds++; }
+      }
       last_pcg = its;
       pcg_total += its;
       tm.lap(2);
@@ -233,9 +251,13 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
       }
       accepted++;
       err = err_new;
-      acinv = schur_setup(ph, c, 0.0);
-      tm.lap(1);
-      dnorm = schur_solve(ph, c, G, 0.0, acinv, &its);
+      {
+        const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref + its_ref / 2 + 8);
+        acinv = schur_setup(ph, c, 0.0, ft, rebuild, acinv);
+        tm.lap(1);
+        dnorm = schur_solve(ph, c, G, 0.0, acinv, &its, ft, false);
+        if (rebuild) { its_ref = its; prec_builds++; }
+      }
       last_pcg = its;
       pcg_total += its;
       tm.lap(2);
@@ -245,6 +267,9 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
     res->iterations = iter; res->accepted = accepted; res->relin = relin; res->chi2_evals = nchi;
     res->pcg_iters = pcg_total; res->chi2_initial = err0; res->chi2_final = err;
     res->trace_n = iter < kTraceCap ? iter : kTraceCap;
+    res->status = prec_builds;
+    tm.acc[5] = (unsigned long long)prec_builds * 1000000ull;
+    tm.flush(res);
   }
 }
 
@@ -260,6 +285,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
   c.bar = bars + team * 32;
   c.bar_target = 0;
   c.red_slot = 0;
+  c.smem_cache_ok = 0;
   c.smem = smem;
   for (int g = team; g < n_graphs; g += n_teams) {
     __syncthreads();
@@ -393,33 +419,35 @@ static int upload(Solver* s) {
     if (kSmRc + 6 * c.nc * 8 > kSmemBytes) { g_err = "graph too large for the coarse-space shared-memory buffer"; return -1; }
     DevGraph& d = s->hd;
     std::memset(&d, 0, sizeof(d));
-    d.N = c.N; d.M = c.M; d.Epl = c.Epl; d.Epf = c.Epf; d.Elp = c.Elp; d.ntile = c.ntile; d.nblk = c.nblk; d.nc = c.nc;
-    d.SP = kCoarseSpacing; d.n_upart = c.n_upart; d.n_ypart = c.n_ypart; d.nce = c.nce; d.ngrp = c.ngrp;
+    d.N = c.N; d.M = c.M; d.Epl = c.Epl; d.Epf = c.Epf; d.Elp = c.Elp; d.ntile = c.ntile; d.ntile_pl = c.ntile_pl; d.nslot = c.nslot;
+    d.nblk = c.nblk; d.nc = c.nc;
+    d.SP = c.SP; d.inv_SP = 1.0 / (double)c.SP; d.n_upart = c.n_upart; d.n_ypart = c.n_ypart; d.nce = c.nce; d.ngrp = c.ngrp;
 #define UP(field) if (s->dupload(&d.field, c.field, &bytes) < 0) return -1
-    UP(pp_pose); UP(pp_plane); UP(pp_ptr); UP(pm2pl); UP(pm_part); UP(ypart_ptr); UP(pp_meas); UP(pp_sinf);
+    UP(pp_pose); UP(pp_plane); UP(pp_ptr); UP(pp_end); UP(pm2pl); UP(pm_part); UP(ypart_ptr); UP(tile_ptr); UP(blk_part_ptr);
+    UP(grp_of_slot); UP(pp_meas); UP(pp_sinf);
     UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr);
     UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pf_meas); UP(pf_sinf);
     UP(lp_plane); UP(linc_ptr); UP(linc); UP(lp_meas); UP(lp_sinf);
     UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem);
     UP(ce_ptr); UP(ce_node); UP(ce_plane); UP(ce_lo); UP(ce_hi); UP(n2ce_ptr); UP(n2ce);
 #undef UP
-    const size_t N = c.N, M = c.M, E = c.Epl, T = c.ntile;
+    const size_t N = c.N, M = c.M, E = c.nslot, T = c.ntile, TL = c.ntile_pl;
 #define AL(field, n, name) if (s->dalloc(&d.field, (size_t)(n), name) < 0) return -1
     AL(pose_lin, N * 7, "pose_lin"); AL(pose_trial, N * 7, "pose_trial"); AL(pose_init, N * 7, "pose_init");
     AL(plane_lin, M * 4, "plane_lin"); AL(plane_trial, M * 4, "plane_trial"); AL(plane_init, M * 4, "plane_init");
-    AL(W, T * kWStride, "Wtiles"); AL(Wt, T * kWStride, "Wttiles"); AL(JP, E * 21, "JP"); AL(JL, E * 12, "JL");
+    AL(W, T * kWStride, "Wtiles"); AL(Wt, TL * kWStride, "Wttiles"); AL(JP, E * 21, "JP"); AL(JL, E * 12, "JL");
     AL(PF, (size_t)c.Epf * 120, "PF"); AL(LP, (size_t)c.Elp * 12, "LP");
     AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
-    AL(vl, M * 3, "vl"); AL(dl, M * 3, "dl"); AL(upart, (size_t)c.n_upart * 3, "upart"); AL(ypart, (size_t)c.n_ypart * 6, "ypart");
+    AL(vl, M * 3, "vl"); AL(dl, M * 3, "dl"); AL(upart, (size_t)c.n_upart * 3, "upart"); AL(ypart, 8, "ypart");
     AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc");
     AL(Ac[0], (size_t)36 * c.nc * c.nc, "Ac0"); AL(Ac[1], (size_t)36 * c.nc * c.nc, "Ac1");
     AL(x, N * 6, "x"); AL(r, N * 6, "r"); AL(z, N * 6, "z"); AL(q, N * 6, "q"); AL(b, N * 6, "b");
-    AL(pv[0], N * 6, "pv0"); AL(pv[1], N * 6, "pv1");
+    AL(pv[0], N * 6, "pv0"); AL(pv[1], N * 6, "pv1"); AL(xprev, N * 6, "xprev"); AL(zc, (size_t)6 * c.nc, "zc");
     AL(rcpart[0], (size_t)c.nblk * 12, "rcpart0"); AL(rcpart[1], (size_t)c.nblk * 12, "rcpart1"); AL(qcpart, (size_t)c.nblk * 12, "qcpart");
     AL(red, (size_t)4 * 4 * 1024, "red");
 #undef AL
     CUDA_OK(cudaMemsetAsync(d.W, 0, T * kWStride * sizeof(double), s->stream));
-    CUDA_OK(cudaMemsetAsync(d.Wt, 0, T * kWStride * sizeof(double), s->stream));
+    CUDA_OK(cudaMemsetAsync(d.Wt, 0, TL * kWStride * sizeof(double), s->stream));
     if (s->dalloc(&s->d_graph, 1) < 0 || s->dalloc(&s->d_res, 1) < 0 || s->dalloc(&s->d_trace, 1) < 0 ||
         s->dalloc(&s->d_bar, 32 * 1024) < 0)
       return -1;
@@ -432,10 +460,10 @@ static int upload(Solver* s) {
     for (int p = 0; p < c.N; p++) std::memcpy(&c.pose_val[(size_t)p * 7], s->g.nodes[c.pose_node[p]].v, 7 * sizeof(double));
     for (int l = 0; l < c.M; l++) std::memcpy(&c.plane_val[(size_t)l * 4], s->g.nodes[c.plane_node[l]].v, 4 * sizeof(double));
     if (s->meas_dirty) {
-      for (int e = 0; e < c.Epl; e++) std::memcpy(&c.pp_meas[(size_t)e * 4], s->g.factors[c.pp_fid[e]].meas, 4 * sizeof(double));
+      for (int e = 0; e < c.nslot; e++) if (c.pp_fid[e] >= 0) std::memcpy(&c.pp_meas[(size_t)e * 4], s->g.factors[c.pp_fid[e]].meas, 4 * sizeof(double));
       for (int f = 0; f < c.Epf; f++) std::memcpy(&c.pf_meas[(size_t)f * 6], s->g.factors[c.pf_fid[f]].meas, 6 * sizeof(double));
       for (int f = 0; f < c.Elp; f++) std::memcpy(&c.lp_meas[(size_t)f * 4], s->g.factors[c.lp_fid[f]].meas, 4 * sizeof(double));
-      if (c.Epl) CUDA_OK(cudaMemcpyAsync(const_cast<double*>(s->hd.pp_meas), c.pp_meas.data(), c.pp_meas.size() * 8, cudaMemcpyHostToDevice, s->stream));
+      if (c.nslot) CUDA_OK(cudaMemcpyAsync(const_cast<double*>(s->hd.pp_meas), c.pp_meas.data(), c.pp_meas.size() * 8, cudaMemcpyHostToDevice, s->stream));
       if (c.Epf) CUDA_OK(cudaMemcpyAsync(const_cast<double*>(s->hd.pf_meas), c.pf_meas.data(), c.pf_meas.size() * 8, cudaMemcpyHostToDevice, s->stream));
       if (c.Elp) CUDA_OK(cudaMemcpyAsync(const_cast<double*>(s->hd.lp_meas), c.lp_meas.data(), c.lp_meas.size() * 8, cudaMemcpyHostToDevice, s->stream));
       bytes += (long long)(c.pp_meas.size() + c.pf_meas.size() + c.lp_meas.size()) * 8;
@@ -467,6 +495,9 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
   p.max_iter = s->prop.max_iterations; p.lambda0 = s->prop.lm_lambda0; p.lambda_factor = s->prop.lm_lambda_factor;
   p.robust_kind = s->robust_kind; p.robust_b = s->robust_b;
   p.pcg_tol = s->opt.pcg_rel_tol; p.pcg_max_iter = s->opt.pcg_max_iter;
+  p.prec_refresh = s->opt.reserved[0] == 1 ? 0 : 1;
+  p.fine_timers = s->opt.reserved[2] == 1 ? 1 : 0;     // reserved[2] = 1: sub-phase timers inside the PCG phases
+  p.warm_start = s->opt.reserved[1] == 1 ? 0 : 1;      // reserved[1] = 1: never warm-start PCG after a rejected step  // reserved[0] = 1: rebuild the preconditioner every solve
   p.mode = mode; p.debug_stage = debug_stage; p.debug_lambda = debug_lambda; p.restore_init = restore_init;
 }
 
@@ -539,8 +570,9 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
     for (int f = 0; f < s->c.Epf; f++) npr += s->c.pf_j[f] < 0;
     st.n_pose_prior = npr; st.n_odometry = s->c.Epf - npr; st.n_plane_prior = s->c.Elp;
     st.gpu_launches = 1; st.grid_ctas = grid; st.block_threads = kThreads;
-    for (int k = 0; k < 8; k++) st.phase_ms[k] = s->res.phase_ns[k] * 1e-6;
-    s->last_acinv = s->res.status;
+    for (int k = 0; k < 24; k++) st.phase_ms[k] = s->res.phase_ns[k] * 1e-6;
+    if (mode == MODE_DEBUG) s->last_acinv = s->res.status;
+    st.gpu_launches = 1;
   }
   return 0;
 }
@@ -883,19 +915,20 @@ long long pus_debug_fetch(pus_handle h, const char* name, double* out, long long
   if (nm == "grp_mem_ptr") return ints(c.grp_mem_ptr);
   if (nm == "blk_grp_ptr") return ints(c.blk_grp_ptr);
   if (nm == "dims") {
-    double d[10] = {(double)c.N, (double)c.M, (double)c.Epl, (double)c.Epf, (double)c.Elp, (double)c.ntile, (double)c.nblk, (double)c.nc, (double)c.nce, (double)c.ngrp};
-    if (cap >= 10) std::memcpy(out, d, sizeof(d));
-    return 10;
+    double d[12] = {(double)c.N, (double)c.M, (double)c.Epl, (double)c.Epf, (double)c.Elp, (double)c.ntile, (double)c.nblk, (double)c.nc, (double)c.nce, (double)c.ngrp, (double)c.nslot, (double)c.ntile_pl};
+    if (cap >= 12) std::memcpy(out, d, sizeof(d));
+    return 12;
   }
   if (!s->uploaded) { g_err = "nothing uploaded"; return -1; }
-  if (nm == "W" || nm == "Wt") {  // de-tiled: [Epl][18] in pose-major (W) or plane-major (Wt) order
-    size_t n = (size_t)c.ntile * kWStride;
+  if (nm == "W" || nm == "Wt") {  // de-tiled: [slots][18] in pose-major slot order (W) or plane-major order (Wt)
+    const bool pm = (nm == "W");
+    size_t nt = pm ? c.ntile : c.ntile_pl, n = nt * kWStride;
     std::vector<double> tmp(n);
-    if (cudaMemcpy(tmp.data(), nm == "W" ? s->hd.W : s->hd.Wt, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { g_err = "memcpy"; return -1; }
-    long long cnt = (long long)c.Epl * 18;
+    if (cudaMemcpy(tmp.data(), pm ? s->hd.W : s->hd.Wt, n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { g_err = "memcpy"; return -1; }
+    long long cnt = (long long)nt * 32 * 18;
     if (cnt <= cap)
-      for (int e = 0; e < c.Epl; e++)
-        for (int k = 0; k < 18; k++) out[(size_t)e * 18 + k] = tmp[(size_t)(e >> 5) * kWStride + k * 32 + (e & 31)];
+      for (size_t e = 0; e < nt * 32; e++)
+        for (int k = 0; k < 18; k++) out[e * 18 + k] = tmp[(e >> 5) * kWStride + k * 32 + (e & 31)];
     return cnt;
   }
   if (nm == "Acinv") nm = s->last_acinv ? "Ac1" : "Ac0";

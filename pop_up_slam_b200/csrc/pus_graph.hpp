@@ -24,9 +24,12 @@ enum FactorKind { F_POSE_PRIOR = 0, F_ODOMETRY = 1, F_POSE_PLANE = 2, F_PLANE_PR
 
 constexpr int kBlockPoses = 16;            // poses per dense preconditioner block
 constexpr int kBlockDim = 6 * kBlockPoses; // 96
-constexpr int kCoarseSpacing = 64;         // poses between coarse (hat-function) nodes; multiple of kBlockPoses
+constexpr int kCoarseSpacing = 32;         // base spacing (poses) of the coarse hat-function nodes; multiple of kBlockPoses
+constexpr int kMaxCoarseNodes = 256;       // the spacing grows in steps of 32 so that the dense A_c stays <= 1536^2
 constexpr int kTile = 32;                  // edges per warp tile
 constexpr int kWStride = 18 * kTile;       // doubles per W tile
+constexpr int kMaxGrp = 256;               // plane groups per 16-pose block held in shared memory
+constexpr int kMaxPart = 64;               // (tile, pose) partial sums per block held in shared memory
 
 struct HNode {
   int kind = NODE_POSE;
@@ -148,15 +151,18 @@ struct Graph {
 // ------------------------------------------------------------------------------------------------
 struct Compiled {
   int N = 0, M = 0, Epl = 0, Epf = 0, Elp = 0;
-  int ntile = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0;
+  int SP = kCoarseSpacing;
+  int ntile = 0, nslot = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0;
   std::vector<int> pose_node, plane_node;   // idx -> node id
   std::vector<int> node_idx;                // node id -> idx (pose idx or plane idx), -1 dead
   std::vector<double> pose_val, plane_val;  // [N*7], [M*4]
   // pose-plane edges, pose-major
-  std::vector<int> pp_fid, pp_pose, pp_plane, pp_ptr, pm2pl, pm_part, ypart_ptr;
+  // (slot-indexed: every 16-pose block's edges are padded to whole 32-edge tiles; pad slots have pp_pose = -1)
+  std::vector<int> pp_fid, pp_pose, pp_plane, pp_ptr, pm2pl, pm_part, ypart_ptr, tile_ptr, blk_part_ptr, grp_of_slot;
   std::vector<double> pp_meas, pp_sinf;
   // plane-major view
-  std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr;
+  std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr, pp_end;
+  int ntile_pl = 0;
   // pose factors (prior / odometry)
   std::vector<int> pf_fid, pf_i, pf_j, pinc_ptr, pinc;
   std::vector<double> pf_meas, pf_sinf;
@@ -169,7 +175,8 @@ struct Compiled {
   std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
 };
 
-inline int coarse_nodes(int N) { return N <= 1 ? 1 : (N - 1 + kCoarseSpacing - 1) / kCoarseSpacing + 1; }
+inline int coarse_spacing(int N) { return kCoarseSpacing * std::max(1, (N + kCoarseSpacing * kMaxCoarseNodes - 1) / (kCoarseSpacing * kMaxCoarseNodes)); }
+inline int coarse_nodes(int N, int sp) { return N <= 1 ? 1 : (N - 1 + sp - 1) / sp + 1; }
 
 inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   c = Compiled();
@@ -212,60 +219,92 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     }
   }
   c.Epf = (int)c.pf_fid.size(); c.Elp = (int)c.lp_fid.size();
-  // ---- pose-major ordering of the pose-plane edges (stable: insertion order within a pose) ----
+  // ---- pose-major ordering of the pose-plane edges (stable: insertion order within a pose), padded so that
+  //      every 16-pose block owns whole 32-edge tiles ----
   c.Epl = (int)ppf.size();
   const int E = c.Epl;
+  c.nblk = (N + kBlockPoses - 1) / kBlockPoses;
   std::vector<int> order(E);
   for (int i = 0; i < E; i++) order[i] = i;
   std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
     return c.node_idx[g.factors[ppf[a]].nodes[0]] < c.node_idx[g.factors[ppf[b]].nodes[0]];
   });
-  c.pp_fid.resize(E); c.pp_pose.resize(E); c.pp_plane.resize(E);
-  c.pp_meas.resize((size_t)E * 4); c.pp_sinf.resize((size_t)E * 6);
   c.pp_ptr.assign(N + 1, 0);
-  for (int e = 0; e < E; e++) {
-    const HFactor& F = g.factors[ppf[order[e]]];
-    c.pp_fid[e] = ppf[order[e]];
-    c.pp_pose[e] = c.node_idx[F.nodes[0]];
-    c.pp_plane[e] = c.node_idx[F.nodes[1]];
-    std::memcpy(&c.pp_meas[(size_t)e * 4], F.meas, 4 * sizeof(double));
-    std::memcpy(&c.pp_sinf[(size_t)e * 6], F.sinf, 6 * sizeof(double));
-    c.pp_ptr[c.pp_pose[e] + 1]++;
+  c.tile_ptr.assign(c.nblk + 1, 0);
+  {
+    // count edges per pose, then lay the slots out block by block
+    std::vector<int> cnt(N, 0);
+    for (int i = 0; i < E; i++) cnt[c.node_idx[g.factors[ppf[order[i]]].nodes[0]]]++;
+    int slot = 0;
+    for (int k = 0; k < c.nblk; k++) {
+      c.tile_ptr[k] = slot / kTile;
+      int p0 = k * kBlockPoses, p1 = std::min(N, p0 + kBlockPoses);
+      for (int p = p0; p < p1; p++) { c.pp_ptr[p] = slot; slot += cnt[p]; }
+      slot = (slot + kTile - 1) / kTile * kTile;
+    }
+    c.pp_ptr[N] = slot;  // only used as the end of the last pose when it has no padding after it
+    c.tile_ptr[c.nblk] = slot / kTile;
+    c.nslot = slot;
+    // end of pose p's range = start + cnt (pp_ptr[p+1] may include padding): keep an explicit end array in pp_ptr
+    // by storing starts in pp_ptr[0..N) and ends in pose_end
+    c.ntile = slot / kTile;
+    const int slots = c.nslot;
+    c.pp_fid.assign(slots, -1); c.pp_pose.assign(slots, -1); c.pp_plane.assign(slots, 0);
+    c.pp_meas.assign((size_t)slots * 4, 0.0); c.pp_sinf.assign((size_t)slots * 6, 0.0);
+    for (int s2 = 0; s2 < slots; s2++) c.pp_meas[(size_t)s2 * 4] = 1.0;
+    std::vector<int> fill(c.pp_ptr.begin(), c.pp_ptr.begin() + N);
+    for (int i = 0; i < E; i++) {
+      const HFactor& F = g.factors[ppf[order[i]]];
+      int p = c.node_idx[F.nodes[0]];
+      int e = fill[p]++;
+      c.pp_fid[e] = ppf[order[i]];
+      c.pp_pose[e] = p;
+      c.pp_plane[e] = c.node_idx[F.nodes[1]];
+      std::memcpy(&c.pp_meas[(size_t)e * 4], F.meas, 4 * sizeof(double));
+      std::memcpy(&c.pp_sinf[(size_t)e * 6], F.sinf, 6 * sizeof(double));
+    }
+    c.pp_end.assign(N, 0);
+    for (int p = 0; p < N; p++) c.pp_end[p] = c.pp_ptr[p] + cnt[p];
   }
-  for (int p = 0; p < N; p++) c.pp_ptr[p + 1] += c.pp_ptr[p];
-  c.ntile = (E + kTile - 1) / kTile;
-  const int slots = c.ntile * kTile;
-  // partial slots for the pose-major sweep: one per (tile, pose) run
+  const int slots = c.nslot;
+  // partial slots for the pose-major sweep: one per (tile, pose) run, numbered in slot order (block-local ranges)
   c.pm_part.assign(slots, -1);
   c.ypart_ptr.assign(N + 1, 0);
+  c.blk_part_ptr.assign(c.nblk + 1, 0);
   {
-    int np = 0;
-    for (int e = 0; e < E; e++) {
-      bool head = (e % kTile == 0) || (c.pp_pose[e] != c.pp_pose[e - 1]);
-      if (head) { np++; c.ypart_ptr[c.pp_pose[e] + 1]++; }
+    int np = 0, prev = -1;
+    for (int e = 0; e < slots; e++) {
+      int p = c.pp_pose[e];
+      if (p < 0) { prev = -1; continue; }
+      bool head = (e % kTile == 0) || (p != prev);
+      if (head) { np++; c.ypart_ptr[p + 1]++; }
       c.pm_part[e] = np - 1;
+      prev = p;
     }
     c.n_ypart = np;
     for (int p = 0; p < N; p++) c.ypart_ptr[p + 1] += c.ypart_ptr[p];
-    // partial ids are assigned in edge order == pose order, so pose p owns [ypart_ptr[p], ypart_ptr[p+1])
+    for (int k = 0; k <= c.nblk; k++) c.blk_part_ptr[k] = c.ypart_ptr[std::min(N, k * kBlockPoses)];
   }
-  // ---- plane-major view ----
-  std::vector<int> pord(E);
-  for (int i = 0; i < E; i++) pord[i] = i;
+  // ---- plane-major view (slots of its own: dense, E real entries then padding) ----
+  const int pslots = (E + kTile - 1) / kTile * kTile;
+  c.ntile_pl = pslots / kTile;
+  std::vector<int> pord;
+  pord.reserve(E);
+  for (int e = 0; e < slots; e++) if (c.pp_pose[e] >= 0) pord.push_back(e);
   std::stable_sort(pord.begin(), pord.end(), [&](int a, int b) { return c.pp_plane[a] < c.pp_plane[b]; });
-  c.pl2pm.assign(slots, -1); c.pl_plane.assign(slots, -1); c.pl_pose.assign(slots, 0); c.pl_part.assign(slots, -1);
-  c.pm2pl.assign(E, -1);
+  c.pl2pm.assign(pslots, -1); c.pl_plane.assign(pslots, -1); c.pl_pose.assign(pslots, 0); c.pl_part.assign(pslots, -1);
+  c.pm2pl.assign(slots, -1);
   c.pl_ptr.assign(M + 1, 0); c.upart_ptr.assign(M + 1, 0);
   {
     int np = 0;
-    for (int s = 0; s < E; s++) {
-      int e = pord[s];
-      c.pl2pm[s] = e; c.pm2pl[e] = s;
-      c.pl_plane[s] = c.pp_plane[e]; c.pl_pose[s] = c.pp_pose[e];
+    for (int s2 = 0; s2 < E; s2++) {
+      int e = pord[s2];
+      c.pl2pm[s2] = e; c.pm2pl[e] = s2;
+      c.pl_plane[s2] = c.pp_plane[e]; c.pl_pose[s2] = c.pp_pose[e];
       c.pl_ptr[c.pp_plane[e] + 1]++;
-      bool head = (s % kTile == 0) || (c.pl_plane[s] != c.pl_plane[s - 1]);
-      if (head) { np++; c.upart_ptr[c.pl_plane[s] + 1]++; }
-      c.pl_part[s] = np - 1;
+      bool head = (s2 % kTile == 0) || (c.pl_plane[s2] != c.pl_plane[s2 - 1]);
+      if (head) { np++; c.upart_ptr[c.pl_plane[s2] + 1]++; }
+      c.pl_part[s2] = np - 1;
     }
     c.n_upart = np;
     for (int l = 0; l < M; l++) { c.pl_ptr[l + 1] += c.pl_ptr[l]; c.upart_ptr[l + 1] += c.upart_ptr[l]; }
@@ -290,37 +329,45 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     std::vector<int> fill(c.linc_ptr.begin(), c.linc_ptr.end() - 1);
     for (int f = 0; f < c.Elp; f++) c.linc[fill[c.lp_plane[f]]++] = f;
   }
-  // ---- dense-block groups ----
-  c.nblk = (N + kBlockPoses - 1) / kBlockPoses;
+  // ---- dense-block groups: the edges of every pose block grouped by plane ----
   c.blk_grp_ptr.assign(c.nblk + 1, 0);
-  c.grp_mem.resize(E);
+  c.grp_of_slot.assign(slots, 0);
+  c.grp_mem_ptr.clear(); c.grp_mem.clear(); c.grp_plane.clear();
   for (int k = 0; k < c.nblk; k++) {
-    int p0 = k * kBlockPoses, p1 = std::min(N, p0 + kBlockPoses);
-    int e0 = c.pp_ptr[p0], e1 = c.pp_ptr[p1];
-    std::vector<int> es(e1 - e0);
-    for (int e = e0; e < e1; e++) es[e - e0] = e;
+    int e0 = c.tile_ptr[k] * kTile, e1 = c.tile_ptr[k + 1] * kTile;
+    std::vector<int> es;
+    for (int e = e0; e < e1; e++) if (c.pp_pose[e] >= 0) es.push_back(e);
     std::stable_sort(es.begin(), es.end(), [&](int a, int b) { return c.pp_plane[a] < c.pp_plane[b]; });
+    int g0 = (int)c.grp_plane.size();
     for (int i = 0; i < (int)es.size(); i++) {
       if (i == 0 || c.pp_plane[es[i]] != c.pp_plane[es[i - 1]]) {
         c.grp_plane.push_back(c.pp_plane[es[i]]);
-        c.grp_mem_ptr.push_back(e0 + i);
+        c.grp_mem_ptr.push_back((int)c.grp_mem.size());
       }
-      c.grp_mem[e0 + i] = es[i];
+      c.grp_of_slot[es[i]] = (int)c.grp_plane.size() - 1 - g0;
+      c.grp_mem.push_back(es[i]);
     }
     c.blk_grp_ptr[k + 1] = (int)c.grp_plane.size();
+    if (c.blk_grp_ptr[k + 1] - g0 > kMaxGrp || c.blk_part_ptr[k + 1] - c.blk_part_ptr[k] > kMaxPart) {
+      err = "pose block " + std::to_string(k) + " observes too many planes (limits: " + std::to_string(kMaxGrp) +
+            " distinct planes / " + std::to_string(kMaxPart) + " tile runs per 16 poses)";
+      return false;
+    }
   }
-  c.grp_mem_ptr.push_back(E);
+  c.grp_mem_ptr.push_back((int)c.grp_mem.size());
   c.ngrp = (int)c.grp_plane.size();
   // ---- coarse (plane, node) pairs ----
-  c.nc = coarse_nodes(N);
+  c.SP = coarse_spacing(N);
+  const int SPc = c.SP;
+  c.nc = coarse_nodes(N, SPc);
   c.ce_ptr.assign(M + 1, 0);
   for (int l = 0; l < M; l++) {
     int s0 = c.pl_ptr[l], s1 = c.pl_ptr[l + 1];
     int last = -1;
     for (int s = s0; s < s1; s++) {
       int p = c.pl_pose[s];
-      int c0 = p / kCoarseSpacing;
-      int cand[2] = {c0, (p % kCoarseSpacing) ? c0 + 1 : -1};
+      int c0 = p / SPc;
+      int cand[2] = {c0, (p % SPc) ? c0 + 1 : -1};
       for (int q = 0; q < 2; q++) {
         int nd = cand[q];
         if (nd < 0 || nd <= last) continue;
@@ -328,9 +375,9 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
         int lo = s, hi = s;
         // lo: first slot with pose > (nd-1)*SP ; since slots are pose-sorted within the plane, scan
         lo = s0;
-        while (lo < s1 && c.pl_pose[lo] <= (nd - 1) * kCoarseSpacing) lo++;
+        while (lo < s1 && c.pl_pose[lo] <= (nd - 1) * SPc) lo++;
         hi = lo;
-        while (hi < s1 && c.pl_pose[hi] < (nd + 1) * kCoarseSpacing) hi++;
+        while (hi < s1 && c.pl_pose[hi] < (nd + 1) * SPc) hi++;
         c.ce_node.push_back(nd); c.ce_plane.push_back(l); c.ce_lo.push_back(lo); c.ce_hi.push_back(hi);
         last = nd;
       }

@@ -40,6 +40,9 @@ struct LmParams {
   int debug_stage;
   double debug_lambda;
   int restore_init;
+  int prec_refresh;  // 1: lazy preconditioner refresh (default), 0: rebuild for every solve
+  int warm_start;    // 1: PCG starts from the previous step after a rejected LM step
+  int fine_timers;   // 1: sub-phase timers (perturbs the run slightly)
 };
 
 struct LmResult {
@@ -47,7 +50,7 @@ struct LmResult {
   long long pcg_iters;
   double chi2_initial, chi2_final;
   int trace_n, status;
-  unsigned long long phase_ns[8];
+  unsigned long long phase_ns[24];
 };
 
 struct LmTrace {
@@ -56,11 +59,12 @@ struct LmTrace {
 };
 
 struct DevGraph {
-  int N, M, Epl, Epf, Elp, ntile, nblk, nc, SP, n_upart, n_ypart, nce, ngrp;
+  int N, M, Epl, Epf, Elp, ntile, ntile_pl, nslot, nblk, nc, SP, n_upart, n_ypart, nce, ngrp;
+  double inv_SP;
   // vertex values
   double *pose_lin, *pose_trial, *pose_init, *plane_lin, *plane_trial, *plane_init;
   // pose-plane edges (pose-major) and plane-major view
-  const int *pp_pose, *pp_plane, *pp_ptr, *pm2pl, *pm_part, *ypart_ptr;
+  const int *pp_pose, *pp_plane, *pp_ptr, *pp_end, *pm2pl, *pm_part, *ypart_ptr, *tile_ptr, *blk_part_ptr, *grp_of_slot;
   const double *pp_meas, *pp_sinf;
   const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr;
   // pose factors / plane priors
@@ -76,7 +80,7 @@ struct DevGraph {
   double *Hpp, *gp, *Hll, *gl, *Hinv, *vl, *dl;
   double *upart, *ypart;
   double *Binv, *Wc, *Ac[2];
-  double *x, *r, *z, *q, *b, *pv[2];
+  double *x, *r, *z, *q, *b, *pv[2], *xprev, *zc;
   double *rcpart[2], *qcpart;
   double *red;
   LmParams prm;
@@ -90,6 +94,7 @@ struct Ctx {
   unsigned* bar;         // team barrier counter (zeroed by the host before launch)
   unsigned bar_target;   // thread 0 only
   int red_slot;
+  int smem_cache_ok;     // the dense-block cache in shared memory holds this solve's blocks
   unsigned char* smem;   // dynamic shared memory
 };
 
@@ -139,16 +144,30 @@ constexpr int kSmS1 = kSmS0 + kBlockDim * kBlockDim * 8;
 constexpr int kSmWg = kSmS1 + kBlockDim * kBlockDim * 8;
 constexpr int kSmYg = kSmWg + kMaxStage * 18 * 8;
 constexpr int kSmP = kSmYg + kMaxStage * 18 * 8;
-constexpr int kSmHi = kSmP + 36 * 8;
+constexpr int kSmHi = kSmP + 72 * 8;
 constexpr int kSmBuildEnd = kSmHi + 16 * 8;
 // PCG phases: sA, sB [kSlots*96], szc [kSlots][12][8], rc [6*nc]
 constexpr int kSmA = kSmWork;
 constexpr int kSmB = kSmA + kSlots * kBlockDim * 8;
 constexpr int kSmZc = kSmB + kSlots * kBlockDim * 8;
 constexpr int kSmRc = kSmZc + kSlots * 12 * 8 * 8;
-constexpr int kSmemBytes = kSmBuildEnd;              // >= kSmRc + 6*nc*8 is checked on the host
+// fused pose phase (aliases the coarse-residual area): plane-group vectors and (tile, pose) partial sums
+constexpr int kSmVg = kSmRc;
+constexpr int kSmYp = kSmVg + kSlots * kMaxGrp * 3 * 8;
+constexpr int kSmPoseEnd = kSmYp + kSlots * kMaxPart * 6 * 8;
+static_assert(kSmPoseEnd <= kSmBuildEnd, "shared-memory carve-up");
+// PCG: packed-symmetric copies of the owned dense blocks (upper triangle, 4656 doubles each)
+constexpr int kPackedBlock = kBlockDim * (kBlockDim + 1) / 2;
+constexpr int kSmCache = 72 * 1024;                   // after the PCG work area (rc may use up to 72 KB - kSmRc)
+constexpr int kCacheBlocks = 4;
+constexpr int kSmCacheEnd = kSmCache + kCacheBlocks * kPackedBlock * 8;
+constexpr int kSmemBytes = (kSmBuildEnd > kSmCacheEnd ? kSmBuildEnd : kSmCacheEnd);  // >= kSmRc + 6*nc*8 is checked on the host
+static_assert(kSmPoseEnd <= kSmCache, "pose-phase buffers overlap the block cache");
+static_assert(kSmemBytes <= 227 * 1024, "dynamic shared memory");
 
-// deterministic team-wide sum of K (<= 4) values; result broadcast to every thread
+// deterministic team-wide sum of K (<= 4) values; result broadcast to every thread.
+// warp partials -> CTA partial (warp 0) -> global slot -> team barrier -> every CTA's warp 0 sums the
+// per-CTA partials with strided lanes + a shuffle tree (fixed order, so all CTAs get identical bits).
 template <int K>
 __device__ __forceinline__ void team_reduce(Ctx& c, double* red, double* v) {
   double* s = reinterpret_cast<double*>(c.smem + kSmRed);
@@ -159,18 +178,27 @@ __device__ __forceinline__ void team_reduce(Ctx& c, double* red, double* v) {
   if (lane == 0)
     for (int k = 0; k < K; k++) s[warp * 4 + k] = v[k];
   __syncthreads();
-  if (threadIdx.x < K) {
-    double acc = 0;
-    for (int w = 0; w < kWarps; w++) acc += s[w * 4 + threadIdx.x];
-    if (c.tsize > 1) red[((size_t)c.red_slot * c.tsize + c.rank) * 4 + threadIdx.x] = acc;
-    else s[kWarps * 4 + threadIdx.x] = acc;
+  if (warp == 0) {
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      double acc = (lane < kWarps) ? s[lane * 4 + k] : 0.0;
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        if (c.tsize > 1) red[((size_t)c.red_slot * c.tsize + c.rank) * 4 + k] = acc;
+        else s[kWarps * 4 + k] = acc;
+      }
+    }
   }
   if (c.tsize > 1) {
     team_barrier(c);
-    if (threadIdx.x < K) {
-      double acc = 0;
-      for (int r = 0; r < c.tsize; r++) acc += ldc(red + ((size_t)c.red_slot * c.tsize + r) * 4 + threadIdx.x);
-      s[kWarps * 4 + threadIdx.x] = acc;
+    if (warp == 0) {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        double acc = 0;
+        for (int r = lane; r < c.tsize; r += 32) acc += ldc(red + ((size_t)c.red_slot * c.tsize + r) * 4 + k);
+        acc = warp_sum(acc);
+        if (lane == 0) s[kWarps * 4 + k] = acc;
+      }
     }
     c.red_slot = (c.red_slot + 1) & 3;
   }
@@ -212,53 +240,72 @@ __device__ __forceinline__ void inv6(const double* A, double* Ai) {
   for (int i = 0; i < 36; i++) Ai[i] = a[i];
 }
 
-// one pivot step of the blocked Gauss-Jordan inversion for the 6x6 block (i,j):
-//   (k,k): P ; (k,j): P A_kj ; (i,k): -A_ik P ; else A_ij - A_ik P A_kj      (P = A_kk^-1)
+// one entry of a pivot step of the blocked Gauss-Jordan inversion (6x6 blocks, pivot block k, P = A_kk^-1):
+//   (k,k): P ; (k,j): P A_kj ; (i,k): -A_ik P ; else A_ij - A_ik P A_kj
+// (row, col) are scalar indices of the ldm x ldm matrix; `ld` loads a scalar of the source matrix.
 template <typename Load>
-__device__ __forceinline__ void gj_block(Load ld, double* dst, int ldm, int i, int j, int k, const double* P) {
-  double out[36];
-  if (i == k && j == k) {
-    for (int e = 0; e < 36; e++) out[e] = P[e];
-  } else if (i == k) {
-    double B[36];
-    for (int e = 0; e < 36; e++) B[e] = ld((k * 6 + e / 6) * ldm + j * 6 + e % 6);
-    for (int r = 0; r < 6; r++)
-      for (int cc = 0; cc < 6; cc++) {
-        double s = 0;
-        for (int t = 0; t < 6; t++) s += P[r * 6 + t] * B[t * 6 + cc];
-        out[r * 6 + cc] = s;
-      }
-  } else {
-    double A[36], T[36];
-    for (int e = 0; e < 36; e++) A[e] = ld((i * 6 + e / 6) * ldm + k * 6 + e % 6);
-    for (int r = 0; r < 6; r++)
-      for (int cc = 0; cc < 6; cc++) {
-        double s = 0;
-        for (int t = 0; t < 6; t++) s += A[r * 6 + t] * P[t * 6 + cc];
-        T[r * 6 + cc] = s;
-      }
-    if (j == k) {
-      for (int e = 0; e < 36; e++) out[e] = -T[e];
-    } else {
-      for (int e = 0; e < 36; e++) A[e] = ld((k * 6 + e / 6) * ldm + j * 6 + e % 6);
-      for (int r = 0; r < 6; r++)
-        for (int cc = 0; cc < 6; cc++) {
-          double s = ld((i * 6 + r) * ldm + j * 6 + cc);
-          for (int t = 0; t < 6; t++) s -= T[r * 6 + t] * A[t * 6 + cc];
-          out[r * 6 + cc] = s;
-        }
-    }
+__device__ __forceinline__ double gj_entry(Load ld, int ldm, int row, int col, int k, const double* P) {
+  const int i = row / 6, r = row - i * 6, j = col / 6, cc = col - j * 6;
+  if (i == k) {
+    if (j == k) return P[r * 6 + cc];
+    double s = 0;
+#pragma unroll
+    for (int t = 0; t < 6; t++) s += P[r * 6 + t] * ld((k * 6 + t) * ldm + col);
+    return s;
   }
-  for (int e = 0; e < 36; e++) dst[(i * 6 + e / 6) * ldm + j * 6 + e % 6] = out[e];
+  double a[6];
+#pragma unroll
+  for (int t = 0; t < 6; t++) a[t] = ld(row * ldm + k * 6 + t);
+  if (j == k) {
+    double s = 0;
+#pragma unroll
+    for (int t = 0; t < 6; t++) s += a[t] * P[t * 6 + cc];
+    return -s;
+  }
+  double b[6];
+#pragma unroll
+  for (int t = 0; t < 6; t++) b[t] = ld((k * 6 + t) * ldm + col);
+  double s = ld(row * ldm + col);
+#pragma unroll
+  for (int t = 0; t < 6; t++) {
+    double tr = 0;
+#pragma unroll
+    for (int u = 0; u < 6; u++) tr += a[u] * P[u * 6 + t];
+    s -= tr * b[t];
+  }
+  return s;
 }
 
 // ---------------------------------------------------------------------------------------------
 // phases
 // ---------------------------------------------------------------------------------------------
+// phase timer of the lead thread (CTA 0 of the team, thread 0): %globaltimer deltas accumulated in shared
+// memory (a global read-modify-write per lap would itself cost ~1 us on the critical path) and flushed once.
+constexpr int kSmTimer = 640;  // 24 x u64 inside the first KB of dynamic shared memory
+struct Timer {
+  bool on;
+  unsigned long long t0;
+  unsigned long long* acc;
+  __device__ Timer(bool o, unsigned char* smem) : on(o), t0(0), acc(reinterpret_cast<unsigned long long*>(smem + kSmTimer)) {
+    if (on) { for (int i = 0; i < 24; i++) acc[i] = 0; t0 = gtime(); }
+  }
+  __device__ void sync() { if (on) t0 = gtime(); }
+  __device__ void lap(int slot) {
+    if (on) {
+      unsigned long long t = gtime();
+      acc[slot] += t - t0;
+      t0 = t;
+    }
+  }
+  __device__ void flush(LmResult* res) { if (on) for (int i = 0; i < 24; i++) res->phase_ns[i] = acc[i]; }
+};
+
 struct Phase {
   const DevGraph& G;
   Ctx& c;
+  Timer* ft = nullptr;  // optional fine-grained phase timer (lead thread)
   __device__ Phase(const DevGraph& g, Ctx& cc) : G(g), c(cc) {}
+  __device__ __forceinline__ void lap(int slot) { if (ft) ft->lap(slot); }
 
   __device__ __forceinline__ int tid_team() const { return c.rank * kThreads + threadIdx.x; }
   __device__ __forceinline__ int nthr_team() const { return c.tsize * kThreads; }
@@ -276,8 +323,9 @@ struct Phase {
     const int lane = threadIdx.x & 31;
     for (int tile = warp_team(); tile < G.ntile; tile += nwarp_team()) {
       int e = tile * 32 + lane;
-      if (e < G.Epl) {
-        int p = G.pp_pose[e], l = G.pp_plane[e];
+      int p = G.pp_pose[e];
+      if (p >= 0) {
+        int l = G.pp_plane[e];
         double pose[7], pl[4], m[4], si[6];
         for (int i = 0; i < 7; i++) pose[i] = ldc(G.pose_lin + (size_t)p * 7 + i);
         for (int i = 0; i < 4; i++) pl[i] = ldc(G.plane_lin + (size_t)l * 4 + i);
@@ -356,7 +404,7 @@ struct Phase {
     const long long total = (long long)G.N * 42;
     for (long long idx = tid_team(); idx < total; idx += nthr_team()) {
       int p = (int)(idx / 42), en = (int)(idx % 42);
-      int e0 = G.pp_ptr[p], e1 = G.pp_ptr[p + 1];
+      int e0 = G.pp_ptr[p], e1 = G.pp_end[p];
       int i0 = G.pinc_ptr[p], i1 = G.pinc_ptr[p + 1];
       double acc = 0;
       if (en < 36) {
@@ -421,8 +469,9 @@ struct Phase {
     const double* PV = trial ? G.pose_trial : G.pose_lin;
     const double* LV = trial ? G.plane_trial : G.plane_lin;
     double acc = 0;
-    for (int e = tid_team(); e < G.Epl; e += nthr_team()) {
+    for (int e = tid_team(); e < G.nslot; e += nthr_team()) {
       int p = G.pp_pose[e], l = G.pp_plane[e];
+      if (p < 0) continue;
       double pose[7], pl[4], m[4], si[6], r[3];
       for (int i = 0; i < 7; i++) pose[i] = ldc(PV + (size_t)p * 7 + i);
       for (int i = 0; i < 4; i++) pl[i] = ldc(LV + (size_t)l * 4 + i);
@@ -575,11 +624,10 @@ struct Phase {
           for (int e = 0; e < 36; e++) Ps[e] = Pi[e];
         }
         __syncthreads();
-        if (tid < kBlockPoses * kBlockPoses) {
-          double P[36];
-          for (int e = 0; e < 36; e++) P[e] = Ps[e];
-          const double* s = src;
-          gj_block([s](int off) { return s[off]; }, dst, kBlockDim, tid / kBlockPoses, tid % kBlockPoses, kk, P);
+        {
+          const double* sp = src;
+          for (int idx = tid; idx < kBlockDim * kBlockDim; idx += kThreads)
+            dst[idx] = gj_entry([sp](int off) { return sp[off]; }, kBlockDim, idx / kBlockDim, idx % kBlockDim, kk, Ps);
         }
         __syncthreads();
         double* t = src; src = dst; dst = t;
@@ -593,7 +641,7 @@ struct Phase {
   __device__ __forceinline__ double hat(int p, int node) const {
     int d = p - node * G.SP;
     if (d < 0) d = -d;
-    return d >= G.SP ? 0.0 : 1.0 - (double)d / (double)G.SP;
+    return d >= G.SP ? 0.0 : 1.0 - (double)d * G.inv_SP;
   }
 
   // -------- Schur setup, part 3: coarse pairs Wc = P^T W (warp per (plane, node) pair) --------
@@ -690,27 +738,72 @@ struct Phase {
   }
 
   // -------- Schur setup, part 5: invert A_c in HBM (blocked Gauss-Jordan, one team barrier per pivot) ---
-  // returns the index of the buffer holding A_c^-1
+  // Per pivot every CTA stages the pivot row block (6 x ldm), the pivot column block (ldm x 6) and
+  // T = column * P in shared memory, so each entry update costs one global load.  Returns the buffer index
+  // of A_c^-1.
   __device__ int coarse_invert() {
     const int nc = G.nc, ldm = 6 * nc;
     double* Ps = reinterpret_cast<double*>(c.smem + kSmP);
+    double* Rk = reinterpret_cast<double*>(c.smem + kSmWork);  // [6][ldm]
+    double* Tk = Rk + 6 * ldm;                                 // [ldm][6]  (column block times P)
+    const bool staged = (kSmWork + 12 * ldm * 8 <= kSmWg);
+    const int tid = threadIdx.x;
     int cur = 0;
     for (int kk = 0; kk < nc; kk++) {
       const double* src = G.Ac[cur];
       double* dst = G.Ac[cur ^ 1];
       __syncthreads();
-      if (threadIdx.x == 0) {
+      if (tid < 36) Ps[36 + tid] = ldc(src + (size_t)(kk * 6 + tid / 6) * ldm + kk * 6 + tid % 6);
+      if (staged)
+        for (int i = tid; i < 6 * ldm; i += kThreads) Rk[i] = ldc(src + (size_t)(kk * 6 + i / ldm) * ldm + i % ldm);
+      __syncthreads();
+      if (tid == 0) {
         double A[36], Pi[36];
-        for (int e = 0; e < 36; e++) A[e] = ldc(src + (size_t)(kk * 6 + e / 6) * ldm + kk * 6 + e % 6);
+        for (int e = 0; e < 36; e++) A[e] = Ps[36 + e];
         inv6(A, Pi);
         for (int e = 0; e < 36; e++) Ps[e] = Pi[e];
       }
       __syncthreads();
-      double P[36];
-      for (int e = 0; e < 36; e++) P[e] = Ps[e];
-      const long long nb2 = (long long)nc * nc;
-      for (long long b = tid_team(); b < nb2; b += nthr_team())
-        gj_block([src](int off) { return ldc(src + off); }, dst, ldm, (int)(b / nc), (int)(b % nc), kk, P);
+      if (staged) {
+        // this CTA owns a band of rows: T = (pivot column block of the band) * P, then one global load per entry
+        const int R = (ldm + c.tsize - 1) / c.tsize;
+        const int r0 = c.rank * R, r1 = min(ldm, r0 + R);
+        for (int i = tid; i < (r1 - r0) * 6; i += kThreads) {
+          int row = r0 + i / 6, t = i % 6;
+          const double* a = src + (size_t)row * ldm + kk * 6;
+          double acc = 0;
+#pragma unroll
+          for (int sx = 0; sx < 6; sx++) acc += ldc(a + sx) * Ps[sx * 6 + t];
+          Tk[i] = acc;
+        }
+        __syncthreads();
+        const int nel = (r1 - r0) * ldm;
+        for (int e = tid; e < nel; e += kThreads) {
+          const int lr = e / ldm, col = e - lr * ldm, row = r0 + lr;
+          const int i = row / 6, r = row - i * 6, j = col / 6, cc = col - j * 6;
+          const size_t idx = (size_t)row * ldm + col;
+          double out;
+          if (i == kk) {
+            if (j == kk) out = Ps[r * 6 + cc];
+            else {
+              out = 0;
+#pragma unroll
+              for (int t = 0; t < 6; t++) out += Ps[r * 6 + t] * Rk[t * ldm + col];
+            }
+          } else if (j == kk) {
+            out = -Tk[lr * 6 + cc];
+          } else {
+            out = ldc(src + idx);
+#pragma unroll
+            for (int t = 0; t < 6; t++) out -= Tk[lr * 6 + t] * Rk[t * ldm + col];
+          }
+          dst[idx] = out;
+        }
+      } else {
+        const long long nel = (long long)ldm * ldm;
+        for (long long idx = tid_team(); idx < nel; idx += nthr_team())
+          dst[idx] = gj_entry([src](int off) { return ldc(src + off); }, ldm, (int)(idx / ldm), (int)(idx % ldm), kk, Ps);
+      }
       team_barrier(c);
       cur ^= 1;
     }
@@ -718,9 +811,10 @@ struct Phase {
   }
 
   // -------- plane-major sweep: upart = segmented sums of Wt^T * (va + beta*vb)[pose] --------
-  __device__ void sweep_planes(const double* va, const double* vb, double beta) {
+  // (zc != nullptr: the gathered vector also gets its coarse part P*zc added on the fly, see precondition())
+  __device__ void sweep_planes(const double* va, const double* vb, double beta, const double* zc = nullptr) {
     const int lane = threadIdx.x & 31;
-    for (int tile = warp_team(); tile < G.ntile; tile += nwarp_team()) {
+    for (int tile = warp_team(); tile < G.ntile_pl; tile += nwarp_team()) {
       int s = tile * 32 + lane;
       int key = G.pl_plane[s];
       double u[3] = {0, 0, 0};
@@ -729,6 +823,13 @@ struct Phase {
         double x[6];
         for (int a = 0; a < 6; a++) x[a] = ldc(va + (size_t)p * 6 + a);
         if (vb) for (int a = 0; a < 6; a++) x[a] += beta * ldc(vb + (size_t)p * 6 + a);
+        if (zc) {
+          const int c0 = p / G.SP;
+          const double h0 = hat(p, c0), h1 = hat(p, c0 + 1);
+          const double* z0 = zc + (size_t)c0 * 6;
+          const double* z1 = zc + (size_t)min(c0 + 1, G.nc - 1) * 6;
+          for (int a = 0; a < 6; a++) x[a] += h0 * ldc(z0 + a) + h1 * ldc(z1 + a);
+        }
         const double* wt = G.Wt + (size_t)tile * kWStride + lane;
 #pragma unroll
         for (int a = 0; a < 6; a++)
@@ -768,29 +869,6 @@ struct Phase {
     return nrm;
   }
 
-  // -------- pose-major sweep: ypart = segmented sums of W * vl[plane] --------
-  __device__ void sweep_poses() {
-    const int lane = threadIdx.x & 31;
-    for (int tile = warp_team(); tile < G.ntile; tile += nwarp_team()) {
-      int e = tile * 32 + lane;
-      int key = (e < G.Epl) ? G.pp_pose[e] : -1;
-      double y[6] = {0, 0, 0, 0, 0, 0};
-      if (key >= 0) {
-        int l = G.pp_plane[e];
-        double v0 = ldc(G.vl + (size_t)l * 3), v1 = ldc(G.vl + (size_t)l * 3 + 1), v2 = ldc(G.vl + (size_t)l * 3 + 2);
-        const double* w = G.W + (size_t)tile * kWStride + lane;
-#pragma unroll
-        for (int a = 0; a < 6; a++) y[a] = ldc(w + (a * 3) * 32) * v0 + ldc(w + (a * 3 + 1) * 32) * v1 + ldc(w + (a * 3 + 2) * 32) * v2;
-      }
-      seg_suffix_sum<6>(key, y);
-      int pk = __shfl_up_sync(0xffffffffu, key, 1);
-      if (key >= 0 && (lane == 0 || pk != key)) {
-        double* o = G.ypart + (size_t)G.pm_part[e] * 6;
-        for (int a = 0; a < 6; a++) o[a] = y[a];
-      }
-    }
-  }
-
   // number of rounds every CTA of the team runs over its owned pose blocks
   __device__ __forceinline__ int rounds() const { return (G.nblk + c.tsize * kSlots - 1) / (c.tsize * kSlots); }
 
@@ -805,30 +883,6 @@ struct Phase {
     }
   }
 
-  // -------- right-hand side: b = -gp + sum(ypart) ; x = 0 ; r = b ; p = 0 ; rcpart[0] = P^T b --------
-  __device__ void make_rhs() {
-    double* sA = reinterpret_cast<double*>(c.smem + kSmA);
-    const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
-    for (int rd = 0; rd < rounds(); rd++) {
-      int k = c.rank + c.tsize * (slot + kSlots * rd);
-      int p = k * kBlockPoses + u / 6, row = u % 6;
-      bool live = (slot < kSlots) && (k < G.nblk);
-      int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
-      bool on = live && (p < G.N);
-      __syncthreads();
-      if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
-      if (on) {
-        double v = -ldc(G.gp + (size_t)p * 6 + row);
-        for (int t = G.ypart_ptr[p]; t < G.ypart_ptr[p + 1]; t++) v += ldc(G.ypart + (size_t)t * 6 + row);
-        size_t o = (size_t)p * 6 + row;
-        G.b[o] = v; G.r[o] = v; G.x[o] = 0.0; G.pv[0][o] = 0.0; G.pv[1][o] = 0.0; G.z[o] = 0.0; G.q[o] = 0.0;
-        sA[slot * kBlockDim + u] = v;
-      }
-      __syncthreads();
-      if (live) restrict_block(sA, slot, u, k, np, G.rcpart[0]);
-    }
-  }
-
   // -------- PCG: owner part of the direction update p_new = z + beta p_old --------
   __device__ void update_direction(int cur, double beta) {
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
@@ -836,54 +890,201 @@ struct Phase {
       int k = c.rank + c.tsize * (slot + kSlots * rd);
       int p = k * kBlockPoses + u / 6;
       if (slot < kSlots && k < G.nblk && p < G.N) {
-        size_t o = (size_t)p * 6 + u % 6;
-        G.pv[cur ^ 1][o] = ldc(G.z + o) + beta * ldc(G.pv[cur] + o);
+        const int row = u % 6;
+        size_t o = (size_t)p * 6 + row;
+        const int c0 = p / G.SP;
+        G.pv[cur ^ 1][o] = ldc(G.z + o) + beta * ldc(G.pv[cur] + o) + hat(p, c0) * ldc(G.zc + (size_t)c0 * 6 + row) +
+                           hat(p, c0 + 1) * ldc(G.zc + (size_t)min(c0 + 1, G.nc - 1) * 6 + row);
       }
     }
   }
 
-  // -------- PCG: q = S p for owned poses (given ypart), qcpart = P^T q, returns partial p.q --------
-  __device__ double apply_pose_side(const double* pvec, double lambda, double* qout, double* qc) {
+  // -------- fused pose phase, per owned 16-pose block and entirely inside the owning CTA:
+  //   1. v_g  = Hll^-1 * (sum of the plane-major partials of plane g)     [apply]   or   Hll^-1 gl   [rhs]
+  //   2. y    = segmented sums over the block's pose-major tiles of W_e * v_{g(e)}        (shared memory)
+  //   3. apply: q = (Hpp + lambda diag) p + (pose-pose blocks) p_other - y ; qc = P^T q ; returns partial p.q
+  //      rhs  : b = -gp + y ; x = 0, r = b, p = z = q = 0 ; rcpart[0] = P^T b
+  __device__ double pose_phase(bool rhs, const double* pvec, double lambda, double* qout, double* qc) {
     double* sA = reinterpret_cast<double*>(c.smem + kSmA);
+    double* vg = reinterpret_cast<double*>(c.smem + kSmVg);
+    double* yp = reinterpret_cast<double*>(c.smem + kSmYp);
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
+    const int lane = tid & 31, wis = u >> 5;  // warp within the slot (3 warps per slot)
     double dot = 0;
     for (int rd = 0; rd < rounds(); rd++) {
-      int k = c.rank + c.tsize * (slot + kSlots * rd);
-      int p = k * kBlockPoses + u / 6, row = u % 6;
-      bool live = (slot < kSlots) && (k < G.nblk);
-      int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
-      bool on = live && (p < G.N);
+      const int k = c.rank + c.tsize * (slot + kSlots * rd);
+      const bool live = (slot < kSlots) && (k < G.nblk);
+      const int p = k * kBlockPoses + u / 6, row = u % 6;
+      const int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
+      const bool on = live && (p < G.N);
       __syncthreads();
       if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
-      if (on) {
-        const double* H = G.Hpp + (size_t)p * 36 + row * 6;
-        double pr = 0, v = 0;
-        for (int cc = 0; cc < 6; cc++) {
-          double pc = ldc(pvec + (size_t)p * 6 + cc);
-          double h = ldc(H + cc);
-          if (cc == row) { pr = pc; h *= (1 + lambda); }
-          v += h * pc;
-        }
-        for (int kk = G.pinc_ptr[p]; kk < G.pinc_ptr[p + 1]; kk++) {
-          int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
-          int j = G.pf_j[f];
-          if (j < 0) continue;
-          int o = side ? G.pf_i[f] : j;
-          const double* A12 = G.PF + (size_t)f * 120 + 72;
-          for (int cc = 0; cc < 6; cc++) {
-            double a = side ? ldc(A12 + cc * 6 + row) : ldc(A12 + row * 6 + cc);
-            v += a * ldc(pvec + (size_t)o * 6 + cc);
+      if (live) {
+        // plane-group vectors: one thread per group when the plane has <= 8 partial sums (all loads in one
+        // batch), one warp per group for heavy planes (the ground plane is seen from every pose)
+        const int g0 = G.blk_grp_ptr[k], ng = G.blk_grp_ptr[k + 1] - g0;
+        for (int g = u; g < ng; g += kBlockDim) {
+          const int l = G.grp_plane[g0 + g];
+          double* vo = vg + (slot * kMaxGrp + g) * 3;
+          if (rhs) {
+            for (int b = 0; b < 3; b++) vo[b] = ldc(G.vl + (size_t)l * 3 + b);
+          } else {
+            const int t0 = G.upart_ptr[l], n = G.upart_ptr[l + 1] - t0;
+            if (n <= 8) {
+              double pr[8][3], Hi[9];
+#pragma unroll
+              for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) pr[t][b] = (t < n) ? ldc(G.upart + (size_t)(t0 + t) * 3 + b) : 0.0;
+#pragma unroll
+              for (int t = 0; t < 9; t++) Hi[t] = ldc(G.Hinv + (size_t)l * 9 + t);
+              double uu[3] = {0, 0, 0};
+#pragma unroll
+              for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
+#pragma unroll
+              for (int b = 0; b < 3; b++) vo[b] = Hi[b * 3] * uu[0] + Hi[b * 3 + 1] * uu[1] + Hi[b * 3 + 2] * uu[2];
+            }
           }
         }
-        for (int t = G.ypart_ptr[p]; t < G.ypart_ptr[p + 1]; t++) v -= ldc(G.ypart + (size_t)t * 6 + row);
-        qout[(size_t)p * 6 + row] = v;
-        sA[slot * kBlockDim + u] = v;
-        dot += pr * v;
+        if (!rhs) {
+          for (int g = wis; g < ng; g += 3) {   // heavy planes: a warp sums the partials
+            const int l = G.grp_plane[g0 + g];
+            const int t0 = G.upart_ptr[l], n = G.upart_ptr[l + 1] - t0;
+            if (n <= 8) continue;
+            double uu[3] = {0, 0, 0};
+            for (int tb = t0 + lane; tb < t0 + n; tb += 256) {   // 8 strided partials per lane in flight
+              double pr[8][3];
+#pragma unroll
+              for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) pr[t][b] = (tb + 32 * t < t0 + n) ? ldc(G.upart + (size_t)(tb + 32 * t) * 3 + b) : 0.0;
+#pragma unroll
+              for (int t = 0; t < 8; t++)
+#pragma unroll
+                for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
+            }
+            for (int b = 0; b < 3; b++) uu[b] = warp_sum(uu[b]);
+            if (lane < 3)
+              vg[(slot * kMaxGrp + g) * 3 + lane] = ldc(G.Hinv + (size_t)l * 9 + lane * 3) * uu[0] +
+                                                    ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 1) * uu[1] +
+                                                    ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 2) * uu[2];
+          }
+        }
       }
       __syncthreads();
-      if (live && qc) restrict_block(sA, slot, u, k, np, qc);
+      if (!rhs) lap(21);
+      if (live) {
+        const int t0 = G.tile_ptr[k], nt = G.tile_ptr[k + 1] - t0, part0 = G.blk_part_ptr[k];
+        for (int t = wis; t < nt; t += 3) {
+          const int e = (t0 + t) * 32 + lane;
+          const int key = G.pp_pose[e];
+          double y[6] = {0, 0, 0, 0, 0, 0};
+          if (key >= 0) {
+            const double* v = vg + (slot * kMaxGrp + G.grp_of_slot[e]) * 3;
+            const double v0 = v[0], v1 = v[1], v2 = v[2];
+            const double* w = G.W + (size_t)(t0 + t) * kWStride + lane;
+#pragma unroll
+            for (int a = 0; a < 6; a++) y[a] = ldc(w + (a * 3) * 32) * v0 + ldc(w + (a * 3 + 1) * 32) * v1 + ldc(w + (a * 3 + 2) * 32) * v2;
+          }
+          seg_suffix_sum<6>(key, y);
+          int pk = __shfl_up_sync(0xffffffffu, key, 1);
+          if (key >= 0 && (lane == 0 || pk != key)) {
+            double* o = yp + (slot * kMaxPart + (G.pm_part[e] - part0)) * 6;
+            for (int a = 0; a < 6; a++) o[a] = y[a];
+          }
+        }
+      }
+      __syncthreads();
+      if (!rhs) lap(22);
+      if (on) {
+        const int part0 = G.blk_part_ptr[k];
+        double ysum = 0;
+        for (int t = G.ypart_ptr[p]; t < G.ypart_ptr[p + 1]; t++) ysum += yp[(slot * kMaxPart + (t - part0)) * 6 + row];
+        const size_t o = (size_t)p * 6 + row;
+        if (rhs) {
+          double v = -ldc(G.gp + o) + ysum;
+          G.b[o] = v; G.r[o] = v; G.x[o] = 0.0; G.pv[0][o] = 0.0; G.pv[1][o] = 0.0; G.z[o] = 0.0; G.q[o] = 0.0;
+          sA[slot * kBlockDim + u] = v;
+        } else {
+          const double* H = G.Hpp + (size_t)p * 36 + row * 6;
+          double pr = 0, v = 0;
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++) {
+            double pc = ldc(pvec + (size_t)p * 6 + cc);
+            double h = ldc(H + cc);
+            if (cc == row) { pr = pc; h *= (1 + lambda); }
+            v += h * pc;
+          }
+          {
+            // pose-pose blocks: the first two neighbours (the odometry chain) are loaded together, the rest loop
+            const int i0 = G.pinc_ptr[p], i1 = G.pinc_ptr[p + 1];
+            int nf = 0, kk = i0;
+            const double* Ab[2] = {nullptr, nullptr};
+            const double* xo[2] = {nullptr, nullptr};
+            int sd[2] = {0, 0};
+            for (; kk < i1 && nf < 2; kk++) {
+              int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
+              int j = G.pf_j[f];
+              if (j < 0) continue;
+              Ab[nf] = G.PF + (size_t)f * 120 + 72;
+              xo[nf] = pvec + (size_t)(side ? G.pf_i[f] : j) * 6;
+              sd[nf] = side;
+              nf++;
+            }
+            double av[2][6], xv[2][6];
+#pragma unroll
+            for (int n2 = 0; n2 < 2; n2++)
+#pragma unroll
+              for (int cc = 0; cc < 6; cc++) {
+                av[n2][cc] = (n2 < nf) ? (sd[n2] ? ldc(Ab[n2] + cc * 6 + row) : ldc(Ab[n2] + row * 6 + cc)) : 0.0;
+                xv[n2][cc] = (n2 < nf) ? ldc(xo[n2] + cc) : 0.0;
+              }
+#pragma unroll
+            for (int n2 = 0; n2 < 2; n2++)
+#pragma unroll
+              for (int cc = 0; cc < 6; cc++) v += av[n2][cc] * xv[n2][cc];
+            for (; kk < i1; kk++) {
+              int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
+              int j = G.pf_j[f];
+              if (j < 0) continue;
+              int oth = side ? G.pf_i[f] : j;
+              const double* A12 = G.PF + (size_t)f * 120 + 72;
+              for (int cc = 0; cc < 6; cc++) {
+                double a = side ? ldc(A12 + cc * 6 + row) : ldc(A12 + row * 6 + cc);
+                v += a * ldc(pvec + (size_t)oth * 6 + cc);
+              }
+            }
+          }
+          v -= ysum;
+          qout[o] = v;
+          sA[slot * kBlockDim + u] = v;
+          dot += pr * v;
+        }
+      }
+      __syncthreads();
+      if (live && (rhs || qc)) restrict_block(sA, slot, u, k, np, rhs ? G.rcpart[0] : qc);
+      if (!rhs) lap(23);
     }
     return dot;
+  }
+
+  // -------- PCG: copy the owned dense blocks (upper triangles) into shared memory for the whole solve ----
+  __device__ void cache_blocks() {
+    double* cache = reinterpret_cast<double*>(c.smem + kSmCache);
+    __syncthreads();
+    for (int ci = 0; ci < kCacheBlocks; ci++) {
+      // cached block ci of this CTA = owned block of (slot = ci % kSlots, round = ci / kSlots)
+      int k = c.rank + c.tsize * ((ci % kSlots) + kSlots * (ci / kSlots));
+      if (k >= G.nblk) continue;
+      const double* B = G.Binv + (size_t)k * kBlockDim * kBlockDim;
+      for (int idx = threadIdx.x; idx < kBlockDim * kBlockDim; idx += kThreads) {
+        int i = idx / kBlockDim, j = idx - i * kBlockDim;
+        if (j >= i) cache[(size_t)ci * kPackedBlock + i * kBlockDim - (i * (i - 1)) / 2 + (j - i)] = ldc(B + idx);
+      }
+    }
+    __syncthreads();
   }
 
   // -------- PCG: x += alpha p ; r -= alpha q ; z = M^-1 r (dense block + coarse) ; returns partial r.z ----
@@ -891,7 +1092,6 @@ struct Phase {
   __device__ double precondition(double alpha, const double* pvec, int acinv, const double* rc_old, double* rc_new,
                                  bool first) {
     double* sA = reinterpret_cast<double*>(c.smem + kSmA);   // r_new per slot
-    double* szc = reinterpret_cast<double*>(c.smem + kSmZc); // [kSlots][12][8]
     double* src = reinterpret_cast<double*>(c.smem + kSmRc); // coarse residual, 6*nc
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
     const int ldm = 6 * G.nc;
@@ -900,22 +1100,58 @@ struct Phase {
     __syncthreads();
     for (int i = tid; i < ldm; i += kThreads) {
       int node = i / 6, row = i % 6;
-      double acc = 0;
+      // blocks with c0 == node feed `node` through their slot 0, blocks with c0 == node-1 through slot 1;
+      // issue all loads before the (fixed-order) sums
+      double va[2][8], vq[2][8];
+#pragma unroll
       for (int side = 0; side < 2; side++) {
-        int cint = node - side;  // interval whose blocks have c0 == cint; they feed `node` through slot `side`
-        if (cint < 0) continue;
-        int k0 = cint * bpn, k1 = min(G.nblk, k0 + bpn);
-        for (int k = k0; k < k1; k++) {
-          double v = ldc(rc_old + (size_t)k * 12 + side * 6 + row);
-          if (!first) v -= alpha * ldc(G.qcpart + (size_t)k * 12 + side * 6 + row);
-          acc += v;
+        int cint = node - side;
+        int k0 = cint * bpn;
+#pragma unroll
+        for (int t = 0; t < 8; t++) {
+          int k = k0 + t;
+          bool ok = (cint >= 0) && (t < bpn) && (k < G.nblk);
+          va[side][t] = ok ? ldc(rc_old + (size_t)k * 12 + side * 6 + row) : 0.0;
+          vq[side][t] = (ok && !first) ? ldc(G.qcpart + (size_t)k * 12 + side * 6 + row) : 0.0;
+        }
+      }
+      double acc = 0;
+#pragma unroll
+      for (int side = 0; side < 2; side++)
+#pragma unroll
+        for (int t = 0; t < 8; t++) acc += va[side][t] - alpha * vq[side][t];
+      if (bpn > 8) {  // (spacing > 128 poses: rare large graphs) remaining blocks, plain loop
+        for (int side = 0; side < 2; side++) {
+          int cint = node - side;
+          if (cint < 0) continue;
+          int k0 = cint * bpn + 8, k1 = min(G.nblk, cint * bpn + bpn);
+          for (int k = k0; k < k1; k++) {
+            double v = ldc(rc_old + (size_t)k * 12 + side * 6 + row);
+            if (!first) v -= alpha * ldc(G.qcpart + (size_t)k * 12 + side * 6 + row);
+            acc += v;
+          }
         }
       }
       src[i] = acc;
     }
     __syncthreads();
+    lap(13);
     const double* Ai = G.Ac[acinv];
     double dot = 0;
+    // coarse part, distributed over the team: one warp per row of A_c^-1.  z is never formed with its coarse
+    // part; r.z = r.z_local + rc.zc (rc = P^T r), and the consumers of z add P*zc on the fly.
+    {
+      const int lane = tid & 31;
+      for (int i = warp_team(); i < ldm; i += nwarp_team()) {
+        const double* arow = Ai + (size_t)i * ldm;
+        double acc = 0;
+#pragma unroll 16
+        for (int j = lane; j < ldm; j += 32) acc += ldc(arow + j) * src[j];
+        acc = warp_sum(acc);
+        if (lane == 0) { G.zc[i] = acc; dot += src[i] * acc; }
+      }
+    }
+    lap(14);
     for (int rd = 0; rd < rounds(); rd++) {
       int k = c.rank + c.tsize * (slot + kSlots * rd);
       int p = k * kBlockPoses + u / 6, row = u % 6;
@@ -929,47 +1165,43 @@ struct Phase {
         size_t o = (size_t)p * 6 + row;
         rn = ldc(G.r + o);
         if (!first) {
-          double pp = ldc(pvec + o);
-          rn -= alpha * ldc(G.q + o);
-          G.x[o] = ldc(G.x + o) + alpha * pp;
+          double pp = ldc(pvec + o), qq = ldc(G.q + o), xx = ldc(G.x + o);
+          rn -= alpha * qq;
+          G.x[o] = xx + alpha * pp;
           G.r[o] = rn;
         }
         sA[slot * kBlockDim + u] = rn;
-      }
-      // coarse part: rows of A_c^-1 for the two nodes bracketing the block
-      if (live) {
-        int c0 = (k * kBlockPoses) / G.SP;
-        int oidx = u / 8, part = u % 8;  // 12 outputs x 8 partial sums
-        int node = c0 + oidx / 6;
-        double acc = 0;
-        if (node < G.nc) {
-          const double* arow = Ai + (size_t)(node * 6 + oidx % 6) * ldm;
-          for (int j = part; j < ldm; j += 8) acc += ldc(arow + j) * src[j];
-        }
-        szc[(slot * 12 + oidx) * 8 + part] = acc;
       }
       __syncthreads();
       if (live) restrict_block(sA, slot, u, k, np, rc_new);
       if (on) {
         // dense block: z_local = Binv[k] r_block (symmetric: read column u)
-        const double* B = G.Binv + (size_t)k * kBlockDim * kBlockDim + u;
         double zl = 0;
-        for (int j = 0; j < kBlockDim; j++) zl += ldc(B + (size_t)j * kBlockDim) * sA[slot * kBlockDim + j];
-        int c0 = (k * kBlockPoses) / G.SP;
-        double z0 = 0, z1 = 0;
-        for (int t = 0; t < 8; t++) { z0 += szc[(slot * 12 + row) * 8 + t]; z1 += szc[(slot * 12 + 6 + row) * 8 + t]; }
-        double zz = zl + hat(p, c0) * z0 + hat(p, c0 + 1) * z1;
-        G.z[(size_t)p * 6 + row] = zz;
-        dot += rn * zz;
+        const int ci = slot + kSlots * rd;
+        if (ci < kCacheBlocks && (c.smem_cache_ok)) {
+          const double* cb = reinterpret_cast<const double*>(c.smem + kSmCache) + (size_t)ci * kPackedBlock;
+          const double* rv = sA + slot * kBlockDim;
+          // rows j < u: element (j,u) ; rows j >= u: element (u,j)
+          for (int j = 0; j < u; j++) zl += cb[j * kBlockDim - (j * (j - 1)) / 2 + (u - j)] * rv[j];
+          const double* cu = cb + u * kBlockDim - (u * (u - 1)) / 2 - u;
+          for (int j = u; j < kBlockDim; j++) zl += cu[j] * rv[j];
+        } else {
+          const double* B = G.Binv + (size_t)k * kBlockDim * kBlockDim + u;
+#pragma unroll 32
+          for (int j = 0; j < kBlockDim; j++) zl += ldc(B + (size_t)j * kBlockDim) * sA[slot * kBlockDim + j];
+        }
+        G.z[(size_t)p * 6 + row] = zl;
+        dot += rn * zl;
       }
     }
+    lap(15);
     return dot;
   }
 
   // -------- |x|^2 over owned poses --------
   __device__ double norm_x() {
     double acc = 0;
-    for (int i = tid_team(); i < G.N * 6; i += nthr_team()) { double v = ldc(G.x + i); acc += v * v; }
+    for (int i = tid_team(); i < G.N * 6; i += nthr_team()) { double v = ldc(G.x + i); acc += v * v; G.xprev[i] = v; }
     return acc;
   }
 

@@ -11,7 +11,7 @@ from pop_up_slam_b200.capi import GpuGraphAPI
 
 pytestmark = pytest.mark.gpu
 
-NB, SP = 16, 64
+NB, SP = 16, 32
 
 
 def make_pair(g, robust=True):
@@ -50,10 +50,12 @@ def test_linearize_and_assembly(robust):
     gp = gpu.debug_fetch("gp", N * 6).reshape(N, 6)
     Hll = gpu.debug_fetch("Hll", M * 9).reshape(M, 3, 3)
     gl = gpu.debug_fetch("gl", M * 3).reshape(M, 3)
-    W = gpu.debug_fetch("W", g.n_pose_plane * 18).reshape(-1, 6, 3)
-    Wt = gpu.debug_fetch("Wt", g.n_pose_plane * 18).reshape(-1, 6, 3)
-    pp_pose = gpu.debug_fetch("pp_pose", g.n_pose_plane).astype(int)
-    pp_plane = gpu.debug_fetch("pp_plane", g.n_pose_plane).astype(int)
+    dims = gpu.debug_fetch("dims", 12).astype(int)
+    nslot, ntile_pl = dims[10], dims[11]
+    W = gpu.debug_fetch("W", nslot * 18).reshape(-1, 6, 3)            # pose-major slots (block-padded)
+    Wt = gpu.debug_fetch("Wt", ntile_pl * 32 * 18).reshape(-1, 6, 3)  # plane-major slots
+    pp_pose = gpu.debug_fetch("pp_pose", nslot).astype(int)
+    pp_plane = gpu.debug_fetch("pp_plane", nslot).astype(int)
     pl2pm = gpu.debug_fetch("pl2pm", 1 << 20).astype(int)
     for p in range(N):
         assert relerr(Hpp[p], A[6 * p:6 * p + 6, 6 * p:6 * p + 6]) < 1e-10
@@ -62,11 +64,15 @@ def test_linearize_and_assembly(robust):
         s = 6 * N + 3 * l
         assert relerr(Hll[l], A[s:s + 3, s:s + 3]) < 1e-10
     assert relerr(gl.reshape(-1), -b[6 * N:]) < 1e-10
-    for e in range(g.n_pose_plane):   # each (pose, plane) pair is observed once in the generator
+    assert (pp_pose >= 0).sum() == g.n_pose_plane
+    for e in range(nslot):   # each (pose, plane) pair is observed once in the generator
         p, l = pp_pose[e], pp_plane[e]
+        if p < 0:
+            assert np.all(W[e] == 0)
+            continue
         ref = A[6 * p:6 * p + 6, 6 * N + 3 * l:6 * N + 3 * l + 3]
         assert np.abs(W[e] - ref).max() <= 1e-10 * max(1.0, np.abs(ref).max())
-    assert np.array_equal(Wt, W[pl2pm[:g.n_pose_plane]])
+    assert np.array_equal(Wt[:g.n_pose_plane], W[pl2pm[:g.n_pose_plane]])
 
 
 def schur_reference(orc, g, lam):
