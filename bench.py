@@ -184,7 +184,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     dev = torch.device("cuda", local_rank)
-    stream = torch.cuda.current_stream(dev)
+    stream = torch.cuda.Stream(dev)          # the library launches on this stream; the CUDA events below are recorded on it
+    torch.cuda.set_stream(stream)
 
     api = GpuGraphAPI(device=local_rank)
     api.set_stream(stream.cuda_stream)

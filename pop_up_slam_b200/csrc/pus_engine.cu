@@ -606,6 +606,14 @@ static int download(Solver** ss, int n) {
   return 0;
 }
 
+// a batch rides on the first handle's stream: the others drop their own stream (if any) and borrow it
+static void adopt_stream(Solver* s, cudaStream_t st) {
+  if (s->stream == st) { return; }
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  s->own_stream = false;
+  s->stream = st;
+}
+
 }  // namespace pus
 
 // ---------------------------------------------------------------------------------------------
@@ -642,11 +650,9 @@ int pus_destroy(pus_handle h) {
 int pus_set_stream(pus_handle h, void* st) {
   NEED(h);
   Solver* s = SV(h);
-  if (s->own_stream && s->stream) { cudaStreamDestroy(s->stream); s->own_stream = false; }
-  s->stream = reinterpret_cast<cudaStream_t>(st);
-  if (!st) { s->stream = nullptr; }
-  else s->own_stream = false;
-  if (!st) s->own_stream = false;
+  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  s->own_stream = false;
+  s->stream = reinterpret_cast<cudaStream_t>(st);  // nullptr: a library-owned stream is created on first use
   return 0;
 }
 
@@ -790,15 +796,20 @@ int pus_set_solver_options(pus_handle h, const pus_solver_options* in) { NEED(h)
 
 int pus_upload(pus_handle h) { NEED(h); return upload(SV(h)); }
 int pus_upload_many(pus_handle* hs, int n) {
+  if (n > 1) {
+    if (ensure_device(SV(hs[0])) < 0) return -1;
+    for (int i = 1; i < n; i++) adopt_stream(SV(hs[i]), SV(hs[0])->stream);
+  }
   for (int i = 0; i < n; i++) if (upload(SV(hs[i])) < 0) return -1;
   return 0;
 }
 static int solve_many(pus_handle* hs, int n, int* iters, int mode, int restore) {
   if (n <= 0) return 0;
   std::vector<Solver*> ss(n);
-  for (int i = 0; i < n; i++) {
-    ss[i] = SV(hs[i]);
-    if (i > 0) { ss[i]->stream = ss[0]->stream; }
+  for (int i = 0; i < n; i++) ss[i] = SV(hs[i]);
+  if (n > 1) {
+    if (ensure_device(ss[0]) < 0) return -1;
+    for (int i = 1; i < n; i++) adopt_stream(ss[i], ss[0]->stream);
   }
   if (launch(ss.data(), n, mode, restore, 0, 0.0) < 0) return -1;
   if (iters) for (int i = 0; i < n; i++) iters[i] = ss[i]->res.iterations;
@@ -830,12 +841,7 @@ int pus_batch_optimize_many(pus_handle* hs, int n, int* iters) {
   if (n <= 0) return 0;
   Solver* s0 = SV(hs[0]);
   if (ensure_device(s0) < 0) return -1;
-  for (int i = 1; i < n; i++) {
-    Solver* s = SV(hs[i]);
-    if (s->own_stream && s->stream && s->stream != s0->stream) { cudaStreamDestroy(s->stream); }
-    s->own_stream = false;
-    s->stream = s0->stream;
-  }
+  for (int i = 1; i < n; i++) adopt_stream(SV(hs[i]), s0->stream);
   if (pus_upload_many(hs, n) < 0) return -1;
   if (solve_many(hs, n, iters, MODE_BATCH, 0) < 0) return -1;
   return pus_download_many(hs, n);
