@@ -251,17 +251,9 @@ def main():
     sync_all()
 
     # ---------------- reduce over ranks ----------------
-    tot_ms = float(sum(ms_res))
-    tot_it = float(sum(iters_res))
-    tot_e2e_s = float(sum(t_e2e))
-    tot_e2e_it = float(sum(iters_e2e))
-    if world > 1:
-        t = torch.tensor([tot_ms, tot_e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        s = torch.tensor([tot_it, tot_e2e_it], device=dev, dtype=torch.float64)
-        dist.all_reduce(s, op=dist.ReduceOp.SUM)
-        tot_ms, tot_e2e_s = t.tolist()
-        tot_it, tot_e2e_it = s.tolist()
+    from pop_up_slam_b200.parallel import reduce_throughput
+    tot_it, tot_ms = reduce_throughput(sum(iters_res), sum(ms_res), world, dev)
+    tot_e2e_it, tot_e2e_s = reduce_throughput(sum(iters_e2e), sum(t_e2e), world, dev)
     value = tot_it / (tot_ms * 1e-3)
     e2e_value = tot_e2e_it / tot_e2e_s
 

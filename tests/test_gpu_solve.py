@@ -211,3 +211,27 @@ def test_popup_fit_matches_oracle():
         ref = capi.popup_fit_frames(O.oracle_lib(), seg_ptr, segs, invK, Ts, 10.0, mode, prefix="orc_")
         for a, b in zip(got, ref):
             assert np.array_equal(a, b)   # float32, same operation order, no FMA contraction: bit-exact
+
+
+def test_gpu_matches_frozen_goldens():
+    """the committed oracle outputs (tests/golden, numeric Jacobians as the reference) without running the oracle"""
+    import json
+    import os
+    gold_all = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "oracle_configs_1_2.json")))
+    for key, gold in gold_all.items():
+        g = gg.make_config(gold["config"], seed=gold["seed"])
+        a = GpuGraphAPI()
+        ids = gg.build_interleaved(a, g)
+        gg.configure(a, g)
+        assert ids["pose_ids"].tolist() == gold["pose_ids"] and ids["plane_ids"].tolist() == gold["plane_ids"]
+        assert [a.node_start(int(i)) for i in list(ids["pose_ids"][:8]) + list(ids["plane_ids"][:8])] == gold["node_starts"]
+        assert [a.factor_row(int(f)) for f in ids["pp_fids"][:16]] == gold["factor_rows"]
+        assert a.batch_optimize() == gold["iterations"]
+        assert a.trace()["accepted"].tolist() == gold["accepted"]
+        c = a.chi2()
+        assert abs(c - gold["chi2_final"]) <= TOL * gold["chi2_final"]
+        P, Pg = a.get_poses(ids["pose_ids"]), np.array(gold["poses"])
+        assert np.abs(P[:, :3] - Pg[:, :3]).max() <= TOL * max(1.0, np.abs(Pg[:, :3]).max())
+        L, Lg = a.get_planes(ids["plane_ids"]), np.array(gold["planes"])
+        sgn = np.sign(np.sum(L * Lg, axis=1))[:, None]
+        assert np.abs(L * sgn - Lg).max() <= TOL

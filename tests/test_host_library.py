@@ -1,0 +1,139 @@
+"""CPU tests of the CUDA library's host side (no compute without a GPU): the C-ABI exports every symbol the header
+declares, the graph container behaves like the reference's (ids, offsets, factor initialisation, edits) -- checked
+against the oracle -- and the graph compiler produces a consistent HBM layout.  Optimise calls must fail loudly
+when no CUDA device is present (there is no CPU fallback)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from oracle_api import OracleAPI
+from pop_up_slam_b200 import capi, geometry as geo, graphgen as gg
+from pop_up_slam_b200.capi import GpuGraphAPI
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def no_gpu():
+    try:
+        import torch
+        return not torch.cuda.is_available()
+    except Exception:
+        return True
+
+
+def test_library_exports_every_declared_symbol():
+    hdr = open(os.path.join(ROOT, "include", "popup_gpu.h")).read()
+    names = sorted(set(re.findall(r"\b(pus_[a-z0-9_]+)\s*\(", hdr)))
+    assert len(names) >= 45
+    lib = capi.load_library()
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+
+
+def test_ids_offsets_and_initialisation_match_oracle():
+    g = gg.make_config(2, seed=0, n_poses=40, n_planes=12)
+    a, o = GpuGraphAPI(), OracleAPI()
+    ia, io = gg.build_interleaved(a, g), gg.build_interleaved(o, g)
+    for k in ("pose_ids", "plane_ids", "pp_fids", "odo_fids"):
+        assert np.array_equal(ia[k], io[k])
+    assert a.num_nodes() == o.num_nodes() and a.num_factors() == o.num_factors()
+    for n in range(a.num_nodes()):
+        assert a.node_start(n) == o.node_start(n)
+    for f in range(a.num_factors()):
+        assert a.factor_row(f) == o.factor_row(f)
+        assert a.factor_nodes(f) == o.factor_nodes(f)
+    # nodes initialised by the factors (slam3d.h:123-137, isam_plane3d.h:252-264) agree to rounding
+    assert np.allclose(a.get_poses(ia["pose_ids"]), o.get_poses(io["pose_ids"]), atol=1e-13)
+    assert np.allclose(a.get_planes(ia["plane_ids"]), o.get_planes(io["plane_ids"]), atol=1e-13)
+    # reverse initialisation: pose1 unknown, pose2 known
+    for api in (a, o):
+        p2 = api.add_pose(geo.T_to_pose7(geo.xyzypr_to_T([1, 2, 0.5, 0.3, 0.1, -0.2])))
+        p1 = api.add_pose(None)
+        api.add_odometry(p1, p2, [0.5, 0.1, 0.0, 0.2, 0.0, 0.05], gg.diag_ut([10] * 6))
+        api._tmp = api.get_pose(p1)
+    assert np.allclose(a._tmp, o._tmp, atol=1e-13)
+    # edits
+    pl = int(ia["plane_ids"][3])
+    nf = len(a.node_factors(pl))
+    assert a.node_factors(pl) == o.node_factors(pl) and nf > 0
+    for api in (a, o):
+        api.remove_factor(int(ia["pp_fids"][2]))
+        api.remove_node(pl)
+    assert a.num_nodes() == o.num_nodes() and a.num_factors() == o.num_factors()
+    assert a.node_start(pl) == -1 and a.factor_row(int(ia["pp_fids"][2])) == -1
+    for n in ia["pose_ids"][-3:]:
+        assert a.node_start(int(n)) == o.node_start(int(n))
+    with pytest.raises(capi.ApiError):
+        a.add_pose_plane(int(ia["pose_ids"][0]), pl, [0, 0, 1, 0], gg.diag_ut([1] * 3))    # removed node
+    with pytest.raises(capi.ApiError):
+        b = GpuGraphAPI()
+        b.add_odometry(b.add_pose(None), b.add_pose(None), np.zeros(6), gg.diag_ut([1] * 6))  # neither pose initialised
+
+
+def test_measurement_update_normalises_planes():
+    a = GpuGraphAPI()
+    p = a.add_pose(geo.T_to_pose7(np.eye(4)))
+    l = a.add_plane(None)
+    f = a.add_pose_plane(p, l, [0, 0, 2.0, -4.0], gg.diag_ut([1, 1, 1]))
+    assert np.allclose(a.get_measurement(f), geo.plane_normalize([0, 0, 2.0, -4.0]))
+    assert np.allclose(a.get_plane(l), geo.plane_normalize([0, 0, 2.0, -4.0]))           # identity pose: plane = measurement
+    a.set_measurement(f, [3.0, 0, 0, -3.0])
+    assert np.allclose(a.get_measurement(f), geo.plane_normalize([1, 0, 0, -1]))
+
+
+@pytest.mark.parametrize("cfg", [1, 2, 3])
+def test_compiled_layout_invariants(cfg):
+    g = gg.make_config(cfg, seed=1)
+    a = GpuGraphAPI()
+    gg.build_bulk(a, g)
+    assert a.lib.pus_debug_compile(a.h) == 0
+    N, M, Epl, Epf, Elp, ntile, nblk, nc, nce, ngrp, nslot, ntile_pl = a.debug_fetch("dims", 12).astype(int)
+    assert (N, M, Epl) == (g.n_poses, g.n_planes, g.n_pose_plane) and Epf == g.n_odometry + 1 and Elp == 1
+    assert nslot == ntile * 32 and nblk == (N + 15) // 16
+    pp_pose = a.debug_fetch("pp_pose", nslot).astype(int)
+    pp_plane = a.debug_fetch("pp_plane", nslot).astype(int)
+    real = pp_pose >= 0
+    assert real.sum() == Epl and np.all(np.diff(pp_pose[real]) >= 0)                       # pose-major order
+    for t in range(ntile):                                                               # tiles never straddle pose blocks
+        blk = set(pp_pose[t * 32:(t + 1) * 32][real[t * 32:(t + 1) * 32]] // 16)
+        assert len(blk) <= 1
+    # the compiled edges are a permutation of the generator's edges
+    fid = a.debug_fetch("pp_fid", nslot).astype(int)
+    assert sorted(fid[real].tolist()) == sorted(set(fid[real].tolist())) and real.sum() == len(set(fid[real].tolist()))
+    pl2pm = a.debug_fetch("pl2pm", ntile_pl * 32).astype(int)
+    assert np.all(np.diff(pp_plane[pl2pm[:Epl]]) >= 0) and set(pl2pm[:Epl]) == set(np.nonzero(real)[0])   # plane-major view
+    # partial-sum slots: one per (tile, pose) run
+    pm_part = a.debug_fetch("pm_part", nslot).astype(int)
+    runs = 0
+    for t in range(ntile):
+        seg = pp_pose[t * 32:(t + 1) * 32]
+        seg = seg[seg >= 0]
+        runs += len(np.unique(seg))
+    assert pm_part.max() + 1 == runs
+    # dense-block groups partition the edges
+    mem = a.debug_fetch("grp_mem", Epl).astype(int)
+    assert sorted(mem.tolist()) == np.nonzero(real)[0].tolist()
+    # coarse (plane, node) pairs cover every edge's two hat nodes
+    ce_plane = a.debug_fetch("ce_plane", nce).astype(int)
+    ce_node = a.debug_fetch("ce_node", nce).astype(int)
+    pairs = set(zip(ce_plane.tolist(), ce_node.tolist()))
+    sp = 32 * max(1, -(-N // (32 * 256)))
+    assert nc == (1 if N <= 1 else (N - 1 + sp - 1) // sp + 1)
+    for p, l in zip(pp_pose[real][::17], pp_plane[real][::17]):
+        assert (l, p // sp) in pairs and ((p % sp == 0) or (l, p // sp + 1) in pairs)
+
+
+@pytest.mark.skipif(not no_gpu(), reason="a CUDA device is present")
+def test_no_cpu_fallback_without_a_gpu():
+    g = gg.make_config(1, seed=0)
+    a = GpuGraphAPI()
+    gg.build_bulk(a, g)
+    gg.configure(a, g)
+    for call in (a.batch_optimize, a.update, a.chi2, a.upload):
+        with pytest.raises(capi.ApiError, match="no CUDA device|CUDA"):
+            call()
+    with pytest.raises(capi.ApiError):
+        capi.popup_fit_frames(a.lib, [0, 1], np.zeros((1, 4), np.float32), np.eye(3, dtype=np.float32), np.eye(4, dtype=np.float32)[None])
