@@ -31,6 +31,7 @@ import numpy as np  # noqa: E402
 from pop_up_slam_b200 import graphgen as gg  # noqa: E402
 
 WORKLOAD = "config3_corridor_5000p_500pl_50000e_huber"
+NCU_DRAM_BYTES_PER_LAUNCH = 702.7e6   # profiles/README.md: the solve is L2-resident, DRAM traffic << algorithmic bytes
 
 
 def roofline_bytes(dims, relin, chi2_evals, pcg_iters):
@@ -284,7 +285,8 @@ def main():
                          "pus_get_poses; wall clock around the call, device synchronised on both sides"},
         "gpu_launches": args.steps * st["gpu_launches"],
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": NCU_DRAM_BYTES_PER_LAUNCH,
+                     "traffic_source": "profiles/r1_c3_ncu_raw.csv (dram__bytes_read.sum + dram__bytes_write.sum, one --set full capture of this workload)",
                      "kernel": "lm_kernel (one persistent launch per solve)", "peak_source": peak_src,
                      "algorithmic_bytes_per_launch": nbytes, "bytes_per_unit": per,
                      "note": "config 3 fits in L2 (W = 7.2 MB): latency/barrier-bound by construction, see profiles/ for the HBM-bound config 5",
