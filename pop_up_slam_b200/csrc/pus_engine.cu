@@ -421,7 +421,7 @@ static int upload(Solver* s) {
     std::memset(&d, 0, sizeof(d));
     d.N = c.N; d.M = c.M; d.Epl = c.Epl; d.Epf = c.Epf; d.Elp = c.Elp; d.ntile = c.ntile; d.ntile_pl = c.ntile_pl; d.nslot = c.nslot;
     d.nblk = c.nblk; d.nc = c.nc;
-    d.SP = c.SP; d.inv_SP = 1.0 / (double)c.SP; d.n_upart = c.n_upart; d.n_ypart = c.n_ypart; d.nce = c.nce; d.ngrp = c.ngrp;
+    d.SP = c.SP; d.inv_SP = 1.0 / (double)c.SP; d.ldmc = 6 * c.nc_pad; d.n_upart = c.n_upart; d.n_ypart = c.n_ypart; d.nce = c.nce; d.ngrp = c.ngrp;
 #define UP(field) if (s->dupload(&d.field, c.field, &bytes) < 0) return -1
     UP(pp_pose); UP(pp_plane); UP(pp_ptr); UP(pp_end); UP(pm2pl); UP(pm_part); UP(ypart_ptr); UP(tile_ptr); UP(blk_part_ptr);
     UP(grp_of_slot); UP(pp_meas); UP(pp_sinf);
@@ -440,7 +440,7 @@ static int upload(Solver* s) {
     AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
     AL(vl, M * 3, "vl"); AL(dl, M * 3, "dl"); AL(upart, (size_t)c.n_upart * 3, "upart"); AL(ypart, 8, "ypart");
     AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc");
-    AL(Ac[0], (size_t)36 * c.nc * c.nc, "Ac0"); AL(Ac[1], (size_t)36 * c.nc * c.nc, "Ac1");
+    AL(Ac[0], (size_t)36 * c.nc_pad * c.nc_pad, "Ac0"); AL(Ac[1], (size_t)36 * c.nc_pad * c.nc_pad, "Ac1");
     AL(x, N * 6, "x"); AL(r, N * 6, "r"); AL(z, N * 6, "z"); AL(q, N * 6, "q"); AL(b, N * 6, "b");
     AL(pv[0], N * 6, "pv0"); AL(pv[1], N * 6, "pv1"); AL(xprev, N * 6, "xprev"); AL(zc, (size_t)6 * c.nc, "zc");
     AL(rcpart[0], (size_t)c.nblk * 12, "rcpart0"); AL(rcpart[1], (size_t)c.nblk * 12, "rcpart1"); AL(qcpart, (size_t)c.nblk * 12, "qcpart");
@@ -504,6 +504,7 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
 static int auto_team(const Solver* s, int limit) {
   if (s->opt.team_ctas > 0) return std::min(std::max(1, s->opt.team_ctas), limit);
   int need = std::max((s->c.ntile + kWarps - 1) / kWarps, (s->c.nblk + kSlots - 1) / kSlots);
+  need = std::max(need, (6 * s->c.nc + kWarps - 1) / kWarps);  // one warp per row of the coarse inverse
   return std::min(std::max(need, 1), limit);
 }
 
@@ -530,6 +531,14 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
     team = std::min(share, need);
     int teams = std::min(n, max_ctas / team);
     grid = teams * team;
+  }
+  // the coarse inversion stages a 48x48 pivot block, T (band x 48) and a 48x256 panel chunk in shared memory
+  for (int i = 0; i < n; i++) {
+    const int ldmc = 6 * ss[i]->c.nc_pad, band = (ldmc + team - 1) / team;
+    if (kSmWork + (2 * 48 * 48 + 2 * (size_t)band * 48 + 48 * 256) * 8 > (size_t)kSmemBytes) {
+      g_err = "team of " + std::to_string(team) + " CTAs is too small for a coarse operator of order " + std::to_string(ldmc);
+      return -1;
+    }
   }
   // per-graph parameter blocks
   std::vector<DevGraph> hg(n);
@@ -923,6 +932,7 @@ long long pus_debug_fetch(pus_handle h, const char* name, double* out, long long
   if (nm == "dims") {
     double d[12] = {(double)c.N, (double)c.M, (double)c.Epl, (double)c.Epf, (double)c.Elp, (double)c.ntile, (double)c.nblk, (double)c.nc, (double)c.nce, (double)c.ngrp, (double)c.nslot, (double)c.ntile_pl};
     if (cap >= 12) std::memcpy(out, d, sizeof(d));
+    if (cap >= 14) { out[12] = c.SP; out[13] = c.nc_pad; }
     return 12;
   }
   if (!s->uploaded) { g_err = "nothing uploaded"; return -1; }

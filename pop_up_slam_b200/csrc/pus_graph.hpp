@@ -24,8 +24,9 @@ enum FactorKind { F_POSE_PRIOR = 0, F_ODOMETRY = 1, F_POSE_PLANE = 2, F_PLANE_PR
 
 constexpr int kBlockPoses = 16;            // poses per dense preconditioner block
 constexpr int kBlockDim = 6 * kBlockPoses; // 96
-constexpr int kCoarseSpacing = 32;         // base spacing (poses) of the coarse hat-function nodes; multiple of kBlockPoses
-constexpr int kMaxCoarseNodes = 256;       // the spacing grows in steps of 32 so that the dense A_c stays <= 1536^2
+constexpr int kCoarseSpacing = 16;         // base spacing (poses) of the coarse hat-function nodes; multiple of kBlockPoses
+constexpr int kMaxCoarseNodes = 320;       // the spacing grows in steps of 16 so that the dense A_c stays <= 1920^2
+constexpr int kPivotNodes = 8;             // coarse nodes per pivot block of the blocked Gauss-Jordan inversion (48 scalars)
 constexpr int kTile = 32;                  // edges per warp tile
 constexpr int kWStride = 18 * kTile;       // doubles per W tile
 constexpr int kMaxGrp = 256;               // plane groups per 16-pose block held in shared memory
@@ -152,6 +153,7 @@ struct Graph {
 struct Compiled {
   int N = 0, M = 0, Epl = 0, Epf = 0, Elp = 0;
   int SP = kCoarseSpacing;
+  int nc_pad = 0;  // nc rounded up to whole pivot blocks; the padding nodes carry identity blocks
   int ntile = 0, nslot = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0;
   std::vector<int> pose_node, plane_node;   // idx -> node id
   std::vector<int> node_idx;                // node id -> idx (pose idx or plane idx), -1 dead
@@ -360,6 +362,7 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   c.SP = coarse_spacing(N);
   const int SPc = c.SP;
   c.nc = coarse_nodes(N, SPc);
+  c.nc_pad = (c.nc + kPivotNodes - 1) / kPivotNodes * kPivotNodes;
   c.ce_ptr.assign(M + 1, 0);
   for (int l = 0; l < M; l++) {
     int s0 = c.pl_ptr[l], s1 = c.pl_ptr[l + 1];

@@ -61,6 +61,7 @@ struct LmTrace {
 struct DevGraph {
   int N, M, Epl, Epf, Elp, ntile, ntile_pl, nslot, nblk, nc, SP, n_upart, n_ypart, nce, ngrp;
   double inv_SP;
+  int ldmc;  // leading dimension of A_c (6 * nc rounded up to whole 48-wide pivot blocks)
   // vertex values
   double *pose_lin, *pose_trial, *pose_init, *plane_lin, *plane_trial, *plane_init;
   // pose-plane edges (pose-major) and plane-major view
@@ -669,11 +670,15 @@ struct Phase {
   // -------- Schur setup, part 4: A_c = P^T S P, one warp per coarse row panel --------
   __device__ void coarse_assemble(double lambda) {
     const int lane = threadIdx.x & 31;
-    const int ldm = 6 * G.nc;
+    const int ldm = G.ldmc;
     double* A = G.Ac[0];
-    for (int a = warp_team(); a < G.nc; a += nwarp_team()) {
+    for (int a = warp_team(); a < ldm / 6; a += nwarp_team()) {
       for (int i = lane; i < 6 * ldm; i += 32) A[(size_t)a * 6 * ldm + i] = 0.0;
       __syncwarp();
+      if (a >= G.nc) {  // padding node: identity block
+        if (lane < 6) A[((size_t)a * 6 + lane) * ldm + a * 6 + lane] = 1.0;
+        continue;
+      }
       // P^T Hpp_d P and pose-pose off-diagonals
       int plo = max(0, (a - 1) * G.SP + 1), phi = min(G.N, (a + 1) * G.SP);
       for (int p = plo; p < phi; p++) {
@@ -737,72 +742,114 @@ struct Phase {
     }
   }
 
-  // -------- Schur setup, part 5: invert A_c in HBM (blocked Gauss-Jordan, one team barrier per pivot) ---
-  // Per pivot every CTA stages the pivot row block (6 x ldm), the pivot column block (ldm x 6) and
-  // T = column * P in shared memory, so each entry update costs one global load.  Returns the buffer index
-  // of A_c^-1.
+  // -------- Schur setup, part 5: invert A_c in HBM: blocked Gauss-Jordan with 48-wide pivot blocks ---------
+  // Step k (pivot block K = 48 rows/cols): every CTA inverts A_KK in shared memory (P), forms T = A[band,K]*P for
+  // the band of rows it owns, then streams the pivot row panel A[K,:] through shared memory in 256-column chunks
+  // and writes   (K,K): P ; (K,j): P A_Kj ; (i,K): -T ; (i,j): A_ij - T A_Kj   to the other buffer.
+  // One team barrier per step; ldm/48 steps.  Returns the index of the buffer holding A_c^-1.
   __device__ int coarse_invert() {
-    const int nc = G.nc, ldm = 6 * nc;
-    double* Ps = reinterpret_cast<double*>(c.smem + kSmP);
-    double* Rk = reinterpret_cast<double*>(c.smem + kSmWork);  // [6][ldm]
-    double* Tk = Rk + 6 * ldm;                                 // [ldm][6]  (column block times P)
-    const bool staged = (kSmWork + 12 * ldm * 8 <= kSmWg);
+    constexpr int PW = 6 * kPivotNodes;   // 48
+    constexpr int CW = 256;               // columns of the pivot row panel staged at a time
+    const int ldm = G.ldmc, nsteps = ldm / PW;
+    double* Pa = reinterpret_cast<double*>(c.smem + kSmWork);  // [PW][PW] pivot block (ping)
+    double* Pb = Pa + PW * PW;                                 // [PW][PW] (pong)
+    double* Ab = Pb + PW * PW;                                 // [band][PW] the band's slice of the pivot column block
+    const int R = (ldm + c.tsize - 1) / c.tsize;               // rows per CTA
+    double* Tb = Ab + (size_t)R * PW;                          // [band][PW]  T = A[band,K] * P
+    double* Rc = Tb + (size_t)R * PW;                          // [PW][CW] chunk of the pivot row panel
     const int tid = threadIdx.x;
+    const int r0 = min(ldm, c.rank * R), r1 = min(ldm, r0 + R);
     int cur = 0;
-    for (int kk = 0; kk < nc; kk++) {
+    for (int k = 0; k < nsteps; k++) {
       const double* src = G.Ac[cur];
       double* dst = G.Ac[cur ^ 1];
+      const int k0 = k * PW;
       __syncthreads();
-      if (tid < 36) Ps[36 + tid] = ldc(src + (size_t)(kk * 6 + tid / 6) * ldm + kk * 6 + tid % 6);
-      if (staged)
-        for (int i = tid; i < 6 * ldm; i += kThreads) Rk[i] = ldc(src + (size_t)(kk * 6 + i / ldm) * ldm + i % ldm);
+      for (int i = tid; i < PW * PW; i += kThreads) Pa[i] = ldc(src + (size_t)(k0 + i / PW) * ldm + k0 + i % PW);
+      for (int i = tid; i < (r1 - r0) * PW; i += kThreads) Ab[i] = ldc(src + (size_t)(r0 + i / PW) * ldm + k0 + i % PW);
       __syncthreads();
-      if (tid == 0) {
-        double A[36], Pi[36];
-        for (int e = 0; e < 36; e++) A[e] = Ps[36 + e];
-        inv6(A, Pi);
-        for (int e = 0; e < 36; e++) Ps[e] = Pi[e];
-      }
-      __syncthreads();
-      if (staged) {
-        // this CTA owns a band of rows: T = (pivot column block of the band) * P, then one global load per entry
-        const int R = (ldm + c.tsize - 1) / c.tsize;
-        const int r0 = c.rank * R, r1 = min(ldm, r0 + R);
-        for (int i = tid; i < (r1 - r0) * 6; i += kThreads) {
-          int row = r0 + i / 6, t = i % 6;
-          const double* a = src + (size_t)row * ldm + kk * 6;
-          double acc = 0;
-#pragma unroll
-          for (int sx = 0; sx < 6; sx++) acc += ldc(a + sx) * Ps[sx * 6 + t];
-          Tk[i] = acc;
+      // Gauss-Jordan inversion of the 48x48 pivot block (SPD: no pivoting), ping-pong, one sync per pivot
+      double* ps = Pa;
+      double* pd = Pb;
+      for (int p = 0; p < PW; p++) {
+        const double piv = 1.0 / ps[p * PW + p];
+        for (int i = tid; i < PW * PW; i += kThreads) {
+          int a = i / PW, b = i - a * PW;
+          double v;
+          if (a == p) v = (b == p) ? piv : ps[p * PW + b] * piv;
+          else if (b == p) v = -ps[a * PW + p] * piv;
+          else v = ps[i] - ps[a * PW + p] * ps[p * PW + b] * piv;
+          pd[i] = v;
         }
         __syncthreads();
-        const int nel = (r1 - r0) * ldm;
-        for (int e = tid; e < nel; e += kThreads) {
-          const int lr = e / ldm, col = e - lr * ldm, row = r0 + lr;
-          const int i = row / 6, r = row - i * 6, j = col / 6, cc = col - j * 6;
-          const size_t idx = (size_t)row * ldm + col;
-          double out;
-          if (i == kk) {
-            if (j == kk) out = Ps[r * 6 + cc];
-            else {
-              out = 0;
-#pragma unroll
-              for (int t = 0; t < 6; t++) out += Ps[r * 6 + t] * Rk[t * ldm + col];
-            }
-          } else if (j == kk) {
-            out = -Tk[lr * 6 + cc];
-          } else {
-            out = ldc(src + idx);
-#pragma unroll
-            for (int t = 0; t < 6; t++) out -= Tk[lr * 6 + t] * Rk[t * ldm + col];
-          }
-          dst[idx] = out;
+        double* t = ps; ps = pd; pd = t;
+      }
+      const double* Pm = ps;  // PW is even, so this is Pa again
+      // coefficient rows: T = A[band,K] * P for ordinary rows, -P for the rows of the pivot block itself, so that
+      // every entry outside the pivot columns is  base - sum_t Cf[row][t] * A[K][col]  (base = A_ij, or 0 in pivot rows)
+      for (int i = tid; i < (r1 - r0) * PW; i += kThreads) {
+        int lr = i / PW, t = i - lr * PW;
+        const int row = r0 + lr;
+        double acc;
+        if (row >= k0 && row < k0 + PW) {
+          acc = -Pm[(row - k0) * PW + t];
+        } else {
+          acc = 0;
+#pragma unroll 8
+          for (int sx = 0; sx < PW; sx++) acc += Ab[lr * PW + sx] * Pm[sx * PW + t];
         }
-      } else {
-        const long long nel = (long long)ldm * ldm;
-        for (long long idx = tid_team(); idx < nel; idx += nthr_team())
-          dst[idx] = gj_entry([src](int off) { return ldc(src + off); }, ldm, (int)(idx / ldm), (int)(idx % ldm), kk, Ps);
+        Tb[i] = acc;
+      }
+      __syncthreads();
+      // pivot columns of the band: (i,K) = -T_i for ordinary rows, (K,K) = P
+      for (int i = tid; i < (r1 - r0) * PW; i += kThreads) {
+        int lr = i / PW, t = i - lr * PW;
+        dst[(size_t)(r0 + lr) * ldm + k0 + t] = -Tb[i];
+      }
+      constexpr int RG = 5;  // rows per register tile (x 2 columns)
+      const int band = r1 - r0, ngrp = (band + RG - 1) / RG;
+      for (int c0 = 0; c0 < ldm; c0 += CW) {
+        const int cw = min(CW, ldm - c0);   // ldm is a multiple of 48, so cw is even
+        for (int i = tid; i < PW * cw; i += kThreads) {
+          int t = i / cw, cc = i - t * cw;
+          Rc[t * CW + cc] = ldc(src + (size_t)(k0 + t) * ldm + c0 + cc);
+        }
+        __syncthreads();
+        const int ncp = cw / 2;
+        for (int task = tid; task < ngrp * ncp; task += kThreads) {
+          const int rg = task / ncp, cp = task - rg * ncp;
+          const int col = c0 + 2 * cp, lr0 = rg * RG;
+          double acc[RG][2];
+#pragma unroll
+          for (int i = 0; i < RG; i++) {
+            const int lr = lr0 + i, row = r0 + lr;
+            const bool live = lr < band, rowK = (row >= k0 && row < k0 + PW);
+            acc[i][0] = (live && !rowK) ? ldc(src + (size_t)row * ldm + col) : 0.0;
+            acc[i][1] = (live && !rowK) ? ldc(src + (size_t)row * ldm + col + 1) : 0.0;
+          }
+#pragma unroll 4
+          for (int t = 0; t < PW; t++) {
+            const double2 rv = *reinterpret_cast<const double2*>(Rc + t * CW + 2 * cp);
+#pragma unroll
+            for (int i = 0; i < RG; i++) {
+              const double cf = Tb[min(lr0 + i, band - 1) * PW + t];
+              acc[i][0] -= cf * rv.x;
+              acc[i][1] -= cf * rv.y;
+            }
+          }
+          const bool colK = (col >= k0 && col < k0 + PW);   // col is even and k0 a multiple of 48: col+1 agrees
+          if (!colK) {
+#pragma unroll
+            for (int i = 0; i < RG; i++) {
+              const int lr = lr0 + i;
+              if (lr < band) {
+                double2 o; o.x = acc[i][0]; o.y = acc[i][1];
+                *reinterpret_cast<double2*>(dst + (size_t)(r0 + lr) * ldm + col) = o;
+              }
+            }
+          }
+        }
+        __syncthreads();
       }
       team_barrier(c);
       cur ^= 1;
@@ -1142,13 +1189,20 @@ struct Phase {
     // part; r.z = r.z_local + rc.zc (rc = P^T r), and the consumers of z add P*zc on the fly.
     {
       const int lane = tid & 31;
-      for (int i = warp_team(); i < ldm; i += nwarp_team()) {
-        const double* arow = Ai + (size_t)i * ldm;
-        double acc = 0;
-#pragma unroll 16
-        for (int j = lane; j < ldm; j += 32) acc += ldc(arow + j) * src[j];
+      const int nw = nwarp_team();
+      for (int i = warp_team(); i < ldm; i += 2 * nw) {   // two rows per pass so both rows' loads are in flight
+        const int i2 = i + nw;
+        const double* arow = Ai + (size_t)i * G.ldmc;
+        const double* brow = Ai + (size_t)min(i2, ldm - 1) * G.ldmc;
+        double acc = 0, acc2 = 0;
+#pragma unroll 8
+        for (int j = lane; j < ldm; j += 32) { double sj = src[j]; acc += ldc(arow + j) * sj; acc2 += ldc(brow + j) * sj; }
         acc = warp_sum(acc);
-        if (lane == 0) { G.zc[i] = acc; dot += src[i] * acc; }
+        acc2 = warp_sum(acc2);
+        if (lane == 0) {
+          G.zc[i] = acc; dot += src[i] * acc;
+          if (i2 < ldm) { G.zc[i2] = acc2; dot += src[i2] * acc2; }
+        }
       }
     }
     lap(14);

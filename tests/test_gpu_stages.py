@@ -11,7 +11,7 @@ from pop_up_slam_b200.capi import GpuGraphAPI
 
 pytestmark = pytest.mark.gpu
 
-NB, SP = 16, 32
+NB, SP = 16, 16
 
 
 def make_pair(g, robust=True):
@@ -118,8 +118,10 @@ def test_schur_operator_and_preconditioner():
             if t > 0:
                 P[6 * p + d, 6 * (c0 + 1) + d] = t
     Ac = P.T @ S @ P
-    Acinv = gpu.debug_fetch("Acinv", 36 * nc * nc).reshape(6 * nc, 6 * nc)
-    assert relerr(Acinv, np.linalg.inv(Ac)) < 1e-7
+    ncp = (nc + 7) // 8 * 8       # A_c is padded to whole 48-wide pivot blocks (identity on the padding)
+    Acinv = gpu.debug_fetch("Acinv", 36 * ncp * ncp).reshape(6 * ncp, 6 * ncp)
+    assert relerr(Acinv[:6 * nc, :6 * nc], np.linalg.inv(Ac)) < 1e-7
+    assert np.allclose(Acinv[6 * nc:, 6 * nc:], np.eye(6 * (ncp - nc))) and np.all(Acinv[:6 * nc, 6 * nc:] == 0)
 
 
 @pytest.mark.parametrize("lam", [1e-6, 1e-2])

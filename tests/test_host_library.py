@@ -120,7 +120,7 @@ def test_compiled_layout_invariants(cfg):
     ce_plane = a.debug_fetch("ce_plane", nce).astype(int)
     ce_node = a.debug_fetch("ce_node", nce).astype(int)
     pairs = set(zip(ce_plane.tolist(), ce_node.tolist()))
-    sp = 32 * max(1, -(-N // (32 * 256)))
+    sp = 16 * max(1, -(-N // (16 * 320)))
     assert nc == (1 if N <= 1 else (N - 1 + sp - 1) // sp + 1)
     for p, l in zip(pp_pose[real][::17], pp_plane[real][::17]):
         assert (l, p // sp) in pairs and ((p % sp == 0) or (l, p // sp + 1) in pairs)
