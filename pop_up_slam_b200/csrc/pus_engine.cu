@@ -149,6 +149,7 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
         if (lead) { res->pcg_iters = its; res->chi2_final = dn; }
       }
     }
+    if (lead) tm.flush(res);
     return;
   }
 
@@ -217,7 +218,7 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
       {
         // refresh the preconditioner only when the last solve needed clearly more iterations than the one right
         // after the previous build (deterministic rule, identical on every CTA)
-        const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref + its_ref / 2 + 8);
+        const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref * P.refresh_pct / 100 + P.refresh_add);
         acinv = schur_setup(ph, c, lambda, ft, rebuild, acinv);
         tm.lap(1);
         dnorm = schur_solve(ph, c, G, lambda, acinv, &its, ft, rejected && P.warm_start);
@@ -252,7 +253,7 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
       accepted++;
       err = err_new;
       {
-        const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref + its_ref / 2 + 8);
+        const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref * P.refresh_pct / 100 + P.refresh_add);
         acinv = schur_setup(ph, c, 0.0, ft, rebuild, acinv);
         tm.lap(1);
         dnorm = schur_solve(ph, c, G, 0.0, acinv, &its, ft, false);
@@ -496,6 +497,8 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
   p.robust_kind = s->robust_kind; p.robust_b = s->robust_b;
   p.pcg_tol = s->opt.pcg_rel_tol; p.pcg_max_iter = s->opt.pcg_max_iter;
   p.prec_refresh = s->opt.reserved[0] == 1 ? 0 : 1;
+  p.refresh_pct = s->opt.reserved[3] > 0 ? s->opt.reserved[3] : 200;   // rebuild when its > pct% of the post-build count + add
+  p.refresh_add = 8;
   p.fine_timers = s->opt.reserved[2] == 1 ? 1 : 0;     // reserved[2] = 1: sub-phase timers inside the PCG phases
   p.warm_start = s->opt.reserved[1] == 1 ? 0 : 1;      // reserved[1] = 1: never warm-start PCG after a rejected step  // reserved[0] = 1: rebuild the preconditioner every solve
   p.mode = mode; p.debug_stage = debug_stage; p.debug_lambda = debug_lambda; p.restore_init = restore_init;

@@ -43,6 +43,7 @@ struct LmParams {
   int prec_refresh;  // 1: lazy preconditioner refresh (default), 0: rebuild for every solve
   int warm_start;    // 1: PCG starts from the previous step after a rejected LM step
   int fine_timers;   // 1: sub-phase timers (perturbs the run slightly)
+  int refresh_pct, refresh_add;  // lazy preconditioner refresh threshold
 };
 
 struct LmResult {
@@ -768,6 +769,7 @@ struct Phase {
       for (int i = tid; i < PW * PW; i += kThreads) Pa[i] = ldc(src + (size_t)(k0 + i / PW) * ldm + k0 + i % PW);
       for (int i = tid; i < (r1 - r0) * PW; i += kThreads) Ab[i] = ldc(src + (size_t)(r0 + i / PW) * ldm + k0 + i % PW);
       __syncthreads();
+      lap(6);
       // Gauss-Jordan inversion of the 48x48 pivot block (SPD: no pivoting), ping-pong, one sync per pivot
       double* ps = Pa;
       double* pd = Pb;
@@ -785,6 +787,7 @@ struct Phase {
         double* t = ps; ps = pd; pd = t;
       }
       const double* Pm = ps;  // PW is even, so this is Pa again
+      lap(7);
       // coefficient rows: T = A[band,K] * P for ordinary rows, -P for the rows of the pivot block itself, so that
       // every entry outside the pivot columns is  base - sum_t Cf[row][t] * A[K][col]  (base = A_ij, or 0 in pivot rows)
       for (int i = tid; i < (r1 - r0) * PW; i += kThreads) {
@@ -806,6 +809,7 @@ struct Phase {
         int lr = i / PW, t = i - lr * PW;
         dst[(size_t)(r0 + lr) * ldm + k0 + t] = -Tb[i];
       }
+      lap(21);
       constexpr int RG = 5;  // rows per register tile (x 2 columns)
       const int band = r1 - r0, ngrp = (band + RG - 1) / RG;
       for (int c0 = 0; c0 < ldm; c0 += CW) {
@@ -851,7 +855,9 @@ struct Phase {
         }
         __syncthreads();
       }
+      lap(22);
       team_barrier(c);
+      lap(23);
       cur ^= 1;
     }
     return cur;
