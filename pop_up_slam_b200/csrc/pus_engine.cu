@@ -4,6 +4,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -52,8 +53,10 @@ __device__ int schur_setup(Phase& ph, Ctx& c, double lambda, Timer& ft, bool reb
 // planes.  Returns |delta|; *its = PCG iterations.
 // `warm`: start from the previous solution (kept in G.xprev) -- used after a rejected LM step, where only lambda changed.
 __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambda, int acinv, int* its, Timer& ft, bool warm) {
-  ph.cache_blocks();
-  c.smem_cache_ok = 1;
+  if (!c.use_tma) {   // (large graphs use that shared memory for the TMA staging buffers instead)
+    ph.cache_blocks();
+    c.smem_cache_ok = 1;
+  }
   ph.pose_phase(true, nullptr, lambda, nullptr, nullptr);  // rhs, with vl = Hll^-1 gl from plane_inverse
   team_barrier(c);
   double v[2];
@@ -124,6 +127,8 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
     res->trace_n = 0; res->status = 0; res->chi2_initial = 0; res->chi2_final = 0;
     for (int i = 0; i < 24; i++) res->phase_ns[i] = 0;
   }
+  c.use_tma = (P.tma_mode == 1) || (P.tma_mode == 0 && G.ntile_pl > 2 * c.tsize * kWarps);
+  c.smem_cache_ok = 0;
   if (P.restore_init) { ph.restore_init(); team_barrier(c); }
   if (P.mode == MODE_CHI2) {
     double e = ph.chi2(false);
@@ -275,7 +280,7 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs, int n_graphs, int team_ctas, unsigned* bars) {
-  extern __shared__ __align__(16) unsigned char smem[];
+  extern __shared__ __align__(128) unsigned char smem[];
   __shared__ DevGraph sG;
   const int n_teams = gridDim.x / team_ctas;
   const int team = blockIdx.x / team_ctas;
@@ -288,6 +293,21 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
   c.red_slot = 0;
   c.smem_cache_ok = 0;
   c.smem = smem;
+  c.use_tma = 0;
+  c.tma_par = 0;
+  c.gj_par = 0;
+  if (threadIdx.x == 0) {
+    unsigned long long* gbar = reinterpret_cast<unsigned long long*>(smem + kSmGjBar);
+    mbar_init(gbar, 1);
+    mbar_init(gbar + 1, 1);
+  }
+  if ((threadIdx.x & 31) == 0) {
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kSmBar) + (threadIdx.x >> 5) * 2;
+    mbar_init(bar, 1);
+    mbar_init(bar + 1, 1);
+    fence_mbar_init();
+  }
+  __syncthreads();
   for (int g = team; g < n_graphs; g += n_teams) {
     __syncthreads();
     const int* src = reinterpret_cast<const int*>(graphs + g);
@@ -345,7 +365,9 @@ struct Solver {
     prop.method = 0; prop.epsilon2 = 1e-2; prop.epsilon_abs = 1e-3; prop.epsilon_rel = 1e-5; prop.max_iterations = 500;
     prop.lm_lambda0 = 1e-6; prop.lm_lambda_factor = 10.; prop.mod_update = 1; prop.mod_batch = 100; prop.mod_solve = 1;
     std::memset(&opt, 0, sizeof(opt));
-    opt.pcg_rel_tol = 1e-10; opt.pcg_max_iter = 2000;
+    opt.pcg_rel_tol = 1e-8; opt.pcg_max_iter = 2000;   // 4 decades under the 1e-4 parity bar
+    if (const char* e = std::getenv("PUS_PCG_REL_TOL")) opt.pcg_rel_tol = std::atof(e);  // experiment hooks
+    if (const char* e = std::getenv("PUS_REFRESH_PCT")) opt.reserved[3] = std::atoi(e);
     std::memset(&stats, 0, sizeof(stats));
     std::memset(&res, 0, sizeof(res));
     std::memset(&hd, 0, sizeof(hd));
@@ -441,7 +463,7 @@ static int upload(Solver* s) {
     AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
     AL(vl, M * 3, "vl"); AL(dl, M * 3, "dl"); AL(upart, (size_t)c.n_upart * 3, "upart"); AL(ypart, 8, "ypart");
     AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc");
-    AL(Ac[0], (size_t)36 * c.nc_pad * c.nc_pad, "Ac0"); AL(Ac[1], (size_t)36 * c.nc_pad * c.nc_pad, "Ac1");
+    AL(Ac[0], ac_doubles(6 * c.nc_pad), "Ac0"); AL(Ac[1], ac_doubles(6 * c.nc_pad), "Ac1");
     AL(x, N * 6, "x"); AL(r, N * 6, "r"); AL(z, N * 6, "z"); AL(q, N * 6, "q"); AL(b, N * 6, "b");
     AL(pv[0], N * 6, "pv0"); AL(pv[1], N * 6, "pv1"); AL(xprev, N * 6, "xprev"); AL(zc, (size_t)6 * c.nc, "zc");
     AL(rcpart[0], (size_t)c.nblk * 12, "rcpart0"); AL(rcpart[1], (size_t)c.nblk * 12, "rcpart1"); AL(qcpart, (size_t)c.nblk * 12, "qcpart");
@@ -499,7 +521,8 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
   p.prec_refresh = s->opt.reserved[0] == 1 ? 0 : 1;
   p.refresh_pct = s->opt.reserved[3] > 0 ? s->opt.reserved[3] : 200;   // rebuild when its > pct% of the post-build count + add
   p.refresh_add = 8;
-  p.fine_timers = s->opt.reserved[2] == 1 ? 1 : 0;     // reserved[2] = 1: sub-phase timers inside the PCG phases
+  p.fine_timers = (s->opt.reserved[2] & 1) ? 1 : 0;     // reserved[2] bit 0: sub-phase timers inside the PCG phases
+  p.tma_mode = (s->opt.reserved[2] & 2) ? 1 : ((s->opt.reserved[2] & 4) ? 2 : 0);  // bit 1: always stage tiles by TMA, bit 2: never
   p.warm_start = s->opt.reserved[1] == 1 ? 0 : 1;      // reserved[1] = 1: never warm-start PCG after a rejected step  // reserved[0] = 1: rebuild the preconditioner every solve
   p.mode = mode; p.debug_stage = debug_stage; p.debug_lambda = debug_lambda; p.restore_init = restore_init;
 }
@@ -508,6 +531,7 @@ static int auto_team(const Solver* s, int limit) {
   if (s->opt.team_ctas > 0) return std::min(std::max(1, s->opt.team_ctas), limit);
   int need = std::max((s->c.ntile + kWarps - 1) / kWarps, (s->c.nblk + kSlots - 1) / kSlots);
   need = std::max(need, (6 * s->c.nc + kWarps - 1) / kWarps);  // one warp per row of the coarse inverse
+  need = std::max(need, (6 * s->c.nc_pad + 15) / 16);           // <= two 8-row MMA tiles per CTA in the coarse inversion
   return std::min(std::max(need, 1), limit);
 }
 
@@ -535,10 +559,10 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
     int teams = std::min(n, max_ctas / team);
     grid = teams * team;
   }
-  // the coarse inversion stages a 48x48 pivot block, T (band x 48) and a 48x256 panel chunk in shared memory
+  // the coarse inversion stages a 48x48 pivot block, the band's coefficient rows and a 48x256 panel chunk in shared memory
   for (int i = 0; i < n; i++) {
-    const int ldmc = 6 * ss[i]->c.nc_pad, band = (ldmc + team - 1) / team;
-    if (kSmWork + (2 * 48 * 48 + 2 * (size_t)band * 48 + 48 * 256) * 8 > (size_t)kSmemBytes) {
+    const int ldmc = 6 * ss[i]->c.nc_pad;
+    if (kSmWork + gj_smem_bytes(ldmc, team) > (size_t)kSmemBytes) {
       g_err = "team of " + std::to_string(team) + " CTAs is too small for a coarse operator of order " + std::to_string(ldmc);
       return -1;
     }
@@ -951,6 +975,17 @@ long long pus_debug_fetch(pus_handle h, const char* name, double* out, long long
     return cnt;
   }
   if (nm == "Acinv") nm = s->last_acinv ? "Ac1" : "Ac0";
+  if (nm == "Ac0" || nm == "Ac1") {  // de-tiled: row-major ldm x ldm
+    const int ldm = 6 * c.nc_pad;
+    const size_t n = ac_doubles(ldm);
+    std::vector<double> tmp(n);
+    if (cudaMemcpy(tmp.data(), s->hd.Ac[nm == "Ac1"], n * 8, cudaMemcpyDeviceToHost) != cudaSuccess) { g_err = "memcpy"; return -1; }
+    long long cnt = (long long)ldm * ldm;
+    if (cnt <= cap)
+      for (int r = 0; r < ldm; r++)
+        for (int q = 0; q < ldm; q++) out[(size_t)r * ldm + q] = tmp[ac_index(ldm, r, q)];
+    return cnt;
+  }
   auto it = s->named.find(nm);
   if (it == s->named.end()) { g_err = "unknown buffer " + nm; return -1; }
   long long cnt = (long long)it->second.second;

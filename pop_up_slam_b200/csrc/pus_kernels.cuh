@@ -44,6 +44,7 @@ struct LmParams {
   int warm_start;    // 1: PCG starts from the previous step after a rejected LM step
   int fine_timers;   // 1: sub-phase timers (perturbs the run slightly)
   int refresh_pct, refresh_add;  // lazy preconditioner refresh threshold
+  int tma_mode;      // 0: TMA-staged W/Wt tiles when a warp owns several tiles (large graphs), 1: always, 2: never
 };
 
 struct LmResult {
@@ -97,6 +98,9 @@ struct Ctx {
   unsigned bar_target;   // thread 0 only
   int red_slot;
   int smem_cache_ok;     // the dense-block cache in shared memory holds this solve's blocks
+  int use_tma;           // this graph streams its W / Wt tiles through the per-warp TMA staging buffers
+  unsigned tma_par;      // phase parity of this warp's two staging mbarriers (bit s = stage s)
+  unsigned gj_par;       // phase parity of the coarse inversion's two panel mbarriers
   unsigned char* smem;   // dynamic shared memory
 };
 
@@ -136,10 +140,77 @@ __device__ __forceinline__ double warp_sum(double v) {
   return v;
 }
 
+// ---- TMA (bulk async copy) + mbarrier helpers: one elected lane issues, the whole warp waits ----
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, unsigned count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void fence_mbar_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+// generic-proxy writes (st.global by the lineariser) -> async-proxy reads (cp.async.bulk)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async;" ::: "memory"); }
+__device__ __forceinline__ void tma_load_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  const unsigned b = smem_u32(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(b), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(b)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void tma_copy_1d(void* dst_smem, const void* src_gmem, unsigned bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// 1/x to full double precision without the IEEE division sequence: hardware seed + two Newton steps
+__device__ __forceinline__ double fast_rcp(double x) {
+  double r;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x, r, 1.0);   // seed: ~20 bits; two Newton steps reach double precision
+  r = fma(r, e, r);
+  e = fma(-x, r, 1.0);
+  return fma(r, e, r);
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned parity) {
+  const unsigned b = smem_u32(bar);
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(b), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+
+// FP64 tensor-core MMA, D(8x8) += A(8x4, row) * B(4x8, col): lane holds a = A[lane/4][lane%4], b = B[lane%4][lane/4],
+// c[0..1] = C[lane/4][2*(lane%4) + {0,1}]
+__device__ __forceinline__ void dmma884(double* cacc, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+               : "+d"(cacc[0]), "+d"(cacc[1])
+               : "d"(a), "d"(b));
+}
+
+// blocked Gauss-Jordan inversion of A_c: chunk width and padded shared-memory strides, rows per CTA
+constexpr int kGjChunk = 128, kGjLdT = 52, kGjLdR = kGjChunk + 4, kGjLdP = 52, kGjLdQ = 12;
+// A_c (and its inverse) live in HBM as 48-row x 128-column tiles, each stored with the padded row stride the MMA
+// fragment loads want, so that one bulk copy brings a whole pivot-panel chunk into shared memory ready to use
+constexpr int kGjTile = 48 * kGjLdR;   // doubles per tile
+__host__ __device__ inline int ac_chunks(int ldm) { return (ldm + kGjChunk - 1) / kGjChunk; }
+__host__ __device__ inline size_t ac_index(int ldm, int row, int col) {
+  return ((size_t)(row / 48) * ac_chunks(ldm) + (col / kGjChunk)) * kGjTile + (size_t)(row % 48) * kGjLdR + (col % kGjChunk);
+}
+__host__ __device__ inline size_t ac_doubles(int ldm) { return (size_t)(ldm / 48) * ac_chunks(ldm) * kGjTile; }
+__host__ __device__ inline int gj_band_rows(int ldm, int team) { return 8 * ((ldm / 8 + team - 1) / team); }
+__host__ __device__ inline size_t gj_smem_bytes(int ldm, int team) {
+  const size_t R = gj_band_rows(ldm, team);
+  return (2 * 48 * kGjLdP + 48 * kGjLdQ + R * 48 + R * kGjLdT + 2 * 48 * (size_t)kGjLdR) * 8;   // two panel buffers
+}
+
 // shared-memory carve-up (bytes)
 constexpr int kSmRed = 0;                            // [kWarps][4] + [4] doubles
 constexpr int kSmRedBytes = (kWarps * 4 + 8) * 8;
-constexpr int kSmWork = 1024;                        // start of the phase-specific area
+constexpr int kSmWork = 1024 + 64;                   // start of the phase-specific area
 // dense-block build: S0, S1 (96x96), Wg, Yg (kMaxStage x 18), P (36), Hinv (9)
 constexpr int kSmS0 = kSmWork;
 constexpr int kSmS1 = kSmS0 + kBlockDim * kBlockDim * 8;
@@ -163,8 +234,17 @@ constexpr int kPackedBlock = kBlockDim * (kBlockDim + 1) / 2;
 constexpr int kSmCache = 72 * 1024;                   // after the PCG work area (rc may use up to 72 KB - kSmRc)
 constexpr int kCacheBlocks = 4;
 constexpr int kSmCacheEnd = kSmCache + kCacheBlocks * kPackedBlock * 8;
-constexpr int kSmemBytes = (kSmBuildEnd > kSmCacheEnd ? kSmBuildEnd : kSmCacheEnd);  // >= kSmRc + 6*nc*8 is checked on the host
+constexpr int kSmemBytes = (kSmBuildEnd > kSmCacheEnd ? kSmBuildEnd : kSmCacheEnd);  // (kSmTmaEnd <= kSmCacheEnd)  // >= kSmRc + 6*nc*8 is checked on the host
 static_assert(kSmPoseEnd <= kSmCache, "pose-phase buffers overlap the block cache");
+// TMA staging (large graphs; replaces the block cache): per warp two 4608-byte W / Wt tiles, filled by
+// cp.async.bulk and signalled through one mbarrier per stage
+constexpr int kSmBar = 768;                           // [kWarps][2] mbarriers (u64)
+constexpr int kSmGjBar = 1024;                        // two mbarriers of the coarse inversion's panel pipeline
+constexpr int kSmTma = kSmCache;
+constexpr int kTileBytes = 18 * 32 * 8;
+constexpr int kSmTmaEnd = kSmTma + kWarps * 2 * kTileBytes;
+static_assert(kSmBar + kWarps * 2 * 8 <= kSmGjBar && kSmGjBar + 16 <= kSmWork, "mbarriers overlap the work area");
+static_assert(kSmTmaEnd <= 227 * 1024, "TMA staging buffers");
 static_assert(kSmemBytes <= 227 * 1024, "dynamic shared memory");
 
 // deterministic team-wide sum of K (<= 4) values; result broadcast to every thread.
@@ -283,7 +363,7 @@ __device__ __forceinline__ double gj_entry(Load ld, int ldm, int row, int col, i
 // ---------------------------------------------------------------------------------------------
 // phase timer of the lead thread (CTA 0 of the team, thread 0): %globaltimer deltas accumulated in shared
 // memory (a global read-modify-write per lap would itself cost ~1 us on the critical path) and flushed once.
-constexpr int kSmTimer = 640;  // 24 x u64 inside the first KB of dynamic shared memory
+constexpr int kSmTimer = 576;  // 24 x u64 inside the first KB of dynamic shared memory
 struct Timer {
   bool on;
   unsigned long long t0;
@@ -354,6 +434,7 @@ struct Phase {
         jl[9] = r[0]; jl[10] = r[1]; jl[11] = r[2];
       }
     }
+    fence_proxy_async();  // W / Wt are read back through the async proxy (bulk copies) on large graphs
   }
 
   // -------- linearise: pose priors / odometry, plane priors --------
@@ -674,10 +755,10 @@ struct Phase {
     const int ldm = G.ldmc;
     double* A = G.Ac[0];
     for (int a = warp_team(); a < ldm / 6; a += nwarp_team()) {
-      for (int i = lane; i < 6 * ldm; i += 32) A[(size_t)a * 6 * ldm + i] = 0.0;
+      for (int i = lane; i < 6 * ldm; i += 32) A[ac_index(ldm, a * 6 + i / ldm, i % ldm)] = 0.0;
       __syncwarp();
       if (a >= G.nc) {  // padding node: identity block
-        if (lane < 6) A[((size_t)a * 6 + lane) * ldm + a * 6 + lane] = 1.0;
+        if (lane < 6) A[ac_index(ldm, a * 6 + lane, a * 6 + lane)] = 1.0;
         continue;
       }
       // P^T Hpp_d P and pose-pose off-diagonals
@@ -694,7 +775,7 @@ struct Phase {
             int r = en / 6, cc = en % 6;
             double v = ldc(G.Hpp + (size_t)p * 36 + en);
             if (r == cc) v *= (1 + lambda);
-            { double* dstp = &A[((size_t)a * 6 + r) * ldm + bnode * 6 + cc]; *dstp = ldc(dstp) + (ha * hb * v); }
+            { double* dstp = &A[ac_index(ldm, a * 6 + r, bnode * 6 + cc)]; *dstp = ldc(dstp) + (ha * hb * v); }
           }
         }
         for (int kk = G.pinc_ptr[p]; kk < G.pinc_ptr[p + 1]; kk++) {
@@ -712,7 +793,7 @@ struct Phase {
               int r = en / 6, cc = en % 6;
               // block (p, o) of Hpp: A12 if p is side 0, A12^T otherwise
               double v = side ? ldc(G.PF + (size_t)f * 120 + 72 + cc * 6 + r) : ldc(G.PF + (size_t)f * 120 + 72 + en);
-              { double* dstp = &A[((size_t)a * 6 + r) * ldm + bnode * 6 + cc]; *dstp = ldc(dstp) + (ha * hb * v); }
+              { double* dstp = &A[ac_index(ldm, a * 6 + r, bnode * 6 + cc)]; *dstp = ldc(dstp) + (ha * hb * v); }
             }
           }
         }
@@ -736,11 +817,12 @@ struct Phase {
             int r = en / 6, cc = en % 6;
             const double* wb = G.Wc + (size_t)ceb * 18 + cc * 3;
             double v = Y[r * 3] * ldc(wb) + Y[r * 3 + 1] * ldc(wb + 1) + Y[r * 3 + 2] * ldc(wb + 2);
-            { double* dstp = &A[((size_t)a * 6 + r) * ldm + bnode * 6 + cc]; *dstp = ldc(dstp) - (v); }
+            { double* dstp = &A[ac_index(ldm, a * 6 + r, bnode * 6 + cc)]; *dstp = ldc(dstp) - (v); }
           }
         }
       }
     }
+    fence_proxy_async();  // A_c is read back by bulk copies in coarse_invert()
   }
 
   // -------- Schur setup, part 5: invert A_c in HBM: blocked Gauss-Jordan with 48-wide pivot blocks ---------
@@ -750,111 +832,207 @@ struct Phase {
   // One team barrier per step; ldm/48 steps.  Returns the index of the buffer holding A_c^-1.
   __device__ int coarse_invert() {
     constexpr int PW = 6 * kPivotNodes;   // 48
-    constexpr int CW = 256;               // columns of the pivot row panel staged at a time
+    constexpr int CW = kGjChunk;          // columns of the pivot row panel staged at a time
+    constexpr int LDT = kGjLdT, LDR = kGjLdR;  // padded strides: the DMMA fragment loads are bank-conflict free
     const int ldm = G.ldmc, nsteps = ldm / PW;
-    double* Pa = reinterpret_cast<double*>(c.smem + kSmWork);  // [PW][PW] pivot block (ping)
-    double* Pb = Pa + PW * PW;                                 // [PW][PW] (pong)
-    double* Ab = Pb + PW * PW;                                 // [band][PW] the band's slice of the pivot column block
-    const int R = (ldm + c.tsize - 1) / c.tsize;               // rows per CTA
-    double* Tb = Ab + (size_t)R * PW;                          // [band][PW]  T = A[band,K] * P
-    double* Rc = Tb + (size_t)R * PW;                          // [PW][CW] chunk of the pivot row panel
-    const int tid = threadIdx.x;
+    constexpr int LDP = kGjLdP, LDQ = kGjLdQ;
+    double* Pa = reinterpret_cast<double*>(c.smem + kSmWork);  // [PW][LDP] pivot block (ping)
+    double* Pb = Pa + PW * LDP;                                // [PW][LDP] (pong); ends up holding the inverse
+    double* TQ = Pb + PW * LDP;                                // [PW][LDQ] coefficient columns of the inner block step
+    const int R = gj_band_rows(ldm, c.tsize);                  // rows per CTA (whole 8-row MMA tiles)
+    double* Ab = TQ + PW * LDQ;                                // [band][PW] the band's slice of the pivot column block
+    double* Tn = Ab + (size_t)R * PW;                          // [band][LDT]  -(A[band,K] * P)   (+P in pivot rows)
+    double* Rc = Tn + (size_t)R * LDT;                         // [2][PW][LDR] chunks of the pivot row panel
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int r0 = min(ldm, c.rank * R), r1 = min(ldm, r0 + R);
+    const int band = r1 - r0, mtiles = band / 8;
+    const int fr = lane >> 2, fc = lane & 3;   // MMA fragment coordinates
     int cur = 0;
     for (int k = 0; k < nsteps; k++) {
       const double* src = G.Ac[cur];
       double* dst = G.Ac[cur ^ 1];
       const int k0 = k * PW;
       __syncthreads();
-      for (int i = tid; i < PW * PW; i += kThreads) Pa[i] = ldc(src + (size_t)(k0 + i / PW) * ldm + k0 + i % PW);
-      for (int i = tid; i < (r1 - r0) * PW; i += kThreads) Ab[i] = ldc(src + (size_t)(r0 + i / PW) * ldm + k0 + i % PW);
+      for (int i = tid; i < PW * PW; i += kThreads) Pa[(i / PW) * LDP + i % PW] = ldc(src + ac_index(ldm, k0 + i / PW, k0 + i % PW));
+      for (int i = tid; i < band * PW; i += kThreads) Ab[i] = ldc(src + ac_index(ldm, r0 + i / PW, k0 + i % PW));
       __syncthreads();
       lap(6);
-      // Gauss-Jordan inversion of the 48x48 pivot block (SPD: no pivoting), ping-pong, one sync per pivot
-      double* ps = Pa;
-      double* pd = Pb;
-      for (int p = 0; p < PW; p++) {
-        const double piv = 1.0 / ps[p * PW + p];
-        for (int i = tid; i < PW * PW; i += kThreads) {
-          int a = i / PW, b = i - a * PW;
-          double v;
-          if (a == p) v = (b == p) ? piv : ps[p * PW + b] * piv;
-          else if (b == p) v = -ps[a * PW + p] * piv;
-          else v = ps[i] - ps[a * PW + p] * ps[p * PW + b] * piv;
-          pd[i] = v;
+      // Inversion of the 48x48 pivot block (SPD: no pivoting) by Gauss-Jordan with 8x8 inner blocks.  Per inner
+      // step J: every warp inverts the 8x8 diagonal block in registers (lane = column, shuffles, no block sync),
+      // the first 384 threads form the coefficient columns TQ = -M[:,J] Q (+Q in the rows of J), and the rank-8
+      // update of the other 30 tiles runs on the FP64 tensor cores from one buffer into the other.
+      {
+        double* Mc = Pa;
+        double* Mn = Pb;
+        const int cidx = lane & 7;
+        for (int J = 0; J < PW / 8; J++) {
+          double d[8];
+#pragma unroll
+          for (int a = 0; a < 8; a++) d[a] = Mc[(8 * J + a) * LDP + 8 * J + cidx];
+#pragma unroll
+          for (int pp = 0; pp < 8; pp++) {
+            const double piv = fast_rcp(__shfl_sync(0xffffffffu, d[pp], pp));
+            double f[8];
+#pragma unroll
+            for (int a = 0; a < 8; a++) f[a] = __shfl_sync(0xffffffffu, d[a], pp);
+            const double rs = (cidx == pp) ? piv : d[pp] * piv;
+#pragma unroll
+            for (int a = 0; a < 8; a++)
+              if (a != pp) d[a] = (cidx == pp) ? -f[a] * piv : fma(-f[a], rs, d[a]);
+            d[pp] = rs;
+          }
+          // d[s] = Q[s][cidx]
+          if (tid < PW * 8) {
+            const int i = tid >> 3;   // row of the 48x48 block; column t of TQ is cidx
+            double v;
+            if (i >= 8 * J && i < 8 * J + 8) {
+              const int rr = i - 8 * J;
+              v = d[0];
+#pragma unroll
+              for (int a = 1; a < 8; a++) v = (rr == a) ? d[a] : v;
+            } else {
+              v = 0;
+#pragma unroll
+              for (int sx = 0; sx < 8; sx++) v = fma(-Mc[i * LDP + 8 * J + sx], d[sx], v);
+            }
+            TQ[i * LDQ + cidx] = v;
+            Mn[i * LDP + 8 * J + cidx] = v;   // the pivot columns of the result are TQ itself
+          }
+          __syncthreads();
+          for (int u = warp; u < 30; u += kWarps) {
+            const int mi = u / 5, nj = u - mi * 5, ni = nj + (nj >= J ? 1 : 0);
+            double cacc[2] = {0.0, 0.0};
+            if (mi != J) {
+              const double2 c2 = *reinterpret_cast<const double2*>(Mc + (8 * mi + fr) * LDP + 8 * ni + 2 * fc);
+              cacc[0] = c2.x; cacc[1] = c2.y;
+            }
+#pragma unroll
+            for (int ks = 0; ks < 2; ks++)
+              dmma884(cacc, TQ[(8 * mi + fr) * LDQ + 4 * ks + fc], Mc[(8 * J + 4 * ks + fc) * LDP + 8 * ni + fr]);
+            *reinterpret_cast<double2*>(Mn + (8 * mi + fr) * LDP + 8 * ni + 2 * fc) = make_double2(cacc[0], cacc[1]);
+          }
+          __syncthreads();
+          double* t = Mc; Mc = Mn; Mn = t;
         }
-        __syncthreads();
-        double* t = ps; ps = pd; pd = t;
       }
-      const double* Pm = ps;  // PW is even, so this is Pa again
+      const double* Pm = Pa;  // six inner steps: the result is back in the first buffer
       lap(7);
-      // coefficient rows: T = A[band,K] * P for ordinary rows, -P for the rows of the pivot block itself, so that
-      // every entry outside the pivot columns is  base - sum_t Cf[row][t] * A[K][col]  (base = A_ij, or 0 in pivot rows)
-      for (int i = tid; i < (r1 - r0) * PW; i += kThreads) {
+      // coefficient rows (negated): Tn = -(A[band,K] * P) for ordinary rows, +P for the rows of the pivot block
+      // itself, so that every entry outside the pivot columns is  base + sum_t Tn[row][t] * A[K][col]
+      // (base = A_ij, or 0 in pivot rows), and the pivot columns of the result are Tn itself
+      for (int i = tid; i < band * PW; i += kThreads) {
         int lr = i / PW, t = i - lr * PW;
         const int row = r0 + lr;
         double acc;
         if (row >= k0 && row < k0 + PW) {
-          acc = -Pm[(row - k0) * PW + t];
+          acc = Pm[(row - k0) * LDP + t];
         } else {
           acc = 0;
 #pragma unroll 8
-          for (int sx = 0; sx < PW; sx++) acc += Ab[lr * PW + sx] * Pm[sx * PW + t];
+          for (int sx = 0; sx < PW; sx++) acc -= Ab[lr * PW + sx] * Pm[sx * LDP + t];
         }
-        Tb[i] = acc;
+        Tn[lr * LDT + t] = acc;
+        dst[ac_index(ldm, row, k0 + t)] = acc;
       }
       __syncthreads();
-      // pivot columns of the band: (i,K) = -T_i for ordinary rows, (K,K) = P
-      for (int i = tid; i < (r1 - r0) * PW; i += kThreads) {
-        int lr = i / PW, t = i - lr * PW;
-        dst[(size_t)(r0 + lr) * ldm + k0 + t] = -Tb[i];
-      }
       lap(21);
-      constexpr int RG = 5;  // rows per register tile (x 2 columns)
-      const int band = r1 - r0, ngrp = (band + RG - 1) / RG;
-      for (int c0 = 0; c0 < ldm; c0 += CW) {
-        const int cw = min(CW, ldm - c0);   // ldm is a multiple of 48, so cw is even
-        for (int i = tid; i < PW * cw; i += kThreads) {
-          int t = i / cw, cc = i - t * cw;
-          Rc[t * CW + cc] = ldc(src + (size_t)(k0 + t) * ldm + c0 + cc);
+      // rank-48 update of the band on the FP64 tensor cores.  The pivot row panel A[K,:] streams through two
+      // shared-memory buffers in 128-column chunks (one bulk async copy per row, mbarrier-signalled, the next chunk
+      // in flight while this one is multiplied); warp w owns the chunk's w-th 8-column tile and up to two 8-row
+      // tiles of the band per pass: mma.m8n8k4 with A = Tn fragment, B = panel fragment, C = base (prefetched).
+      const int nchunk = (ldm + CW - 1) / CW;
+      unsigned long long* gbar = reinterpret_cast<unsigned long long*>(c.smem + kSmGjBar);
+      auto issue = [&](int ci) {   // one bulk copy per chunk: tile (k, ci) of the source, padded stride included
+        if (tid == 0) {
+          double* buf = Rc + (ci & 1) * PW * LDR;
+          tma_load_1d(buf, src + ((size_t)k * nchunk + ci) * kGjTile, (unsigned)(kGjTile * 8), gbar + (ci & 1));
         }
-        __syncthreads();
-        const int ncp = cw / 2;
-        for (int task = tid; task < ngrp * ncp; task += kThreads) {
-          const int rg = task / ncp, cp = task - rg * ncp;
-          const int col = c0 + 2 * cp, lr0 = rg * RG;
-          double acc[RG][2];
+      };
+      auto loadC = [&](int ci, int m0, double (*cc)[2]) {
+        const int col = ci * CW + 8 * warp + 2 * fc;
 #pragma unroll
-          for (int i = 0; i < RG; i++) {
-            const int lr = lr0 + i, row = r0 + lr;
-            const bool live = lr < band, rowK = (row >= k0 && row < k0 + PW);
-            acc[i][0] = (live && !rowK) ? ldc(src + (size_t)row * ldm + col) : 0.0;
-            acc[i][1] = (live && !rowK) ? ldc(src + (size_t)row * ldm + col + 1) : 0.0;
-          }
-#pragma unroll 4
-          for (int t = 0; t < PW; t++) {
-            const double2 rv = *reinterpret_cast<const double2*>(Rc + t * CW + 2 * cp);
+        for (int mi = 0; mi < 2; mi++) {
+          const int row = r0 + 8 * (m0 + mi) + fr;
+          const bool ok = (m0 + mi < mtiles) && (ci * CW + 8 * warp < ldm) && !(row >= k0 && row < k0 + PW);
+          double2 v2 = make_double2(0.0, 0.0);
+          if (ok) v2 = __ldcg(reinterpret_cast<const double2*>(src + ac_index(ldm, row, col)));
+          cc[mi][0] = v2.x;
+          cc[mi][1] = v2.y;
+        }
+      };
+      // first tile pair (all there is when the team is large enough): offsets without the per-chunk index math
+      size_t rowoff[2];
+      bool rowld[2];
 #pragma unroll
-            for (int i = 0; i < RG; i++) {
-              const double cf = Tb[min(lr0 + i, band - 1) * PW + t];
-              acc[i][0] -= cf * rv.x;
-              acc[i][1] -= cf * rv.y;
+      for (int mi = 0; mi < 2; mi++) {
+        const int row = r0 + 8 * mi + fr;
+        rowoff[mi] = (size_t)(min(row, ldm - 1) / 48) * nchunk * kGjTile + (size_t)(min(row, ldm - 1) % 48) * LDR + 8 * warp + 2 * fc;
+        rowld[mi] = (mi < mtiles) && !(row >= k0 && row < k0 + PW);
+      }
+      auto loadC0 = [&](int ci, double (*cc)[2]) {
+#pragma unroll
+        for (int mi = 0; mi < 2; mi++) {
+          double2 v2 = make_double2(0.0, 0.0);
+          if (rowld[mi] && (ci * CW + 8 * warp < ldm)) v2 = __ldcg(reinterpret_cast<const double2*>(src + rowoff[mi] + (size_t)ci * kGjTile));
+          cc[mi][0] = v2.x;
+          cc[mi][1] = v2.y;
+        }
+      };
+      double cn[2][2];
+      issue(0);
+      loadC0(0, cn);
+      for (int ci = 0; ci < nchunk; ci++) {
+        if (ci + 1 < nchunk) issue(ci + 1);
+        double acc[2][2] = {{cn[0][0], cn[0][1]}, {cn[1][0], cn[1][1]}};
+        if (ci + 1 < nchunk) loadC0(ci + 1, cn);
+        lap(16);
+        mbar_wait(gbar + (ci & 1), (c.gj_par >> (ci & 1)) & 1u);
+        c.gj_par ^= (1u << (ci & 1));
+        lap(17);
+        const double* buf = Rc + (ci & 1) * PW * LDR;
+        const int col = ci * CW + 8 * warp + 2 * fc;
+        const bool nlive = (ci * CW + 8 * warp < ldm);
+        const bool colK = (col >= k0 && col < k0 + PW);   // pivot columns were written from Tn (whole tiles)
+        for (int m0 = 0; m0 < mtiles; m0 += 2) {
+          if (m0 > 0) loadC(ci, m0, acc);
+          if (nlive) {
+            const bool m1ok = (m0 + 1 < mtiles);
+            const double* ta0 = Tn + (8 * m0 + fr) * LDT + fc;
+            const double* ta1 = Tn + (8 * (m1ok ? m0 + 1 : m0) + fr) * LDT + fc;
+            const double* rbp = buf + fc * LDR + 8 * warp + fr;
+            // three independent accumulator chains per tile (the MMA latency is long, the chain short)
+            double ax[2][2][2] = {{{0, 0}, {0, 0}}, {{0, 0}, {0, 0}}};
+#pragma unroll
+            for (int ks = 0; ks < PW / 12; ks++) {
+#pragma unroll
+              for (int g3 = 0; g3 < 3; g3++) {
+                const int kk = 4 * (ks + g3 * (PW / 12));
+                const double b0 = rbp[kk * LDR];
+                dmma884(g3 == 0 ? acc[0] : ax[g3 - 1][0], ta0[kk], b0);
+                dmma884(g3 == 0 ? acc[1] : ax[g3 - 1][1], ta1[kk], b0);
+              }
             }
-          }
-          const bool colK = (col >= k0 && col < k0 + PW);   // col is even and k0 a multiple of 48: col+1 agrees
-          if (!colK) {
 #pragma unroll
-            for (int i = 0; i < RG; i++) {
-              const int lr = lr0 + i;
-              if (lr < band) {
-                double2 o; o.x = acc[i][0]; o.y = acc[i][1];
-                *reinterpret_cast<double2*>(dst + (size_t)(r0 + lr) * ldm + col) = o;
+            for (int mi = 0; mi < 2; mi++)
+#pragma unroll
+              for (int q = 0; q < 2; q++) acc[mi][q] += ax[0][mi][q] + ax[1][mi][q];
+            if (!colK) {
+              if (m0 == 0) {
+                *reinterpret_cast<double2*>(dst + rowoff[0] + (size_t)ci * kGjTile) = make_double2(acc[0][0], acc[0][1]);
+                if (m1ok) *reinterpret_cast<double2*>(dst + rowoff[1] + (size_t)ci * kGjTile) = make_double2(acc[1][0], acc[1][1]);
+              } else {
+                *reinterpret_cast<double2*>(dst + ac_index(ldm, r0 + 8 * m0 + fr, col)) = make_double2(acc[0][0], acc[0][1]);
+                if (m1ok)
+                  *reinterpret_cast<double2*>(dst + ac_index(ldm, r0 + 8 * (m0 + 1) + fr, col)) = make_double2(acc[1][0], acc[1][1]);
               }
             }
           }
         }
-        __syncthreads();
+        lap(18);
+        __syncthreads();   // the buffer is free for chunk ci + 2
+        lap(19);
       }
+      fence_proxy_async();  // the other CTAs' bulk copies read these rows in the next step
       lap(22);
       team_barrier(c);
       lap(23);
@@ -866,14 +1044,29 @@ struct Phase {
   // -------- plane-major sweep: upart = segmented sums of Wt^T * (va + beta*vb)[pose] --------
   // (zc != nullptr: the gathered vector also gets its coarse part P*zc added on the fly, see precondition())
   __device__ void sweep_planes(const double* va, const double* vb, double beta, const double* zc = nullptr) {
-    const int lane = threadIdx.x & 31;
-    for (int tile = warp_team(); tile < G.ntile_pl; tile += nwarp_team()) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // large graphs: the warp's next Wt tile (4608 contiguous bytes) is fetched by one bulk async copy into the
+    // other staging buffer while the current one is consumed
+    double* buf = reinterpret_cast<double*>(c.smem + kSmTma) + warp * 2 * kWStride;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + warp * 2;
+    const int step = nwarp_team();
+    int st = 0;
+    if (c.use_tma) {
+      __syncwarp();
+      if (lane == 0 && warp_team() < G.ntile_pl) {
+        fence_proxy_async();
+        tma_load_1d(buf, G.Wt + (size_t)warp_team() * kWStride, kTileBytes, bar);
+      }
+    }
+    for (int tile = warp_team(); tile < G.ntile_pl; tile += step, st ^= 1) {
+      if (c.use_tma && lane == 0 && tile + step < G.ntile_pl)
+        tma_load_1d(buf + (st ^ 1) * kWStride, G.Wt + (size_t)(tile + step) * kWStride, kTileBytes, bar + (st ^ 1));
       int s = tile * 32 + lane;
       int key = G.pl_plane[s];
       double u[3] = {0, 0, 0};
+      double x[6] = {0, 0, 0, 0, 0, 0};
       if (key >= 0) {
         int p = G.pl_pose[s];
-        double x[6];
         for (int a = 0; a < 6; a++) x[a] = ldc(va + (size_t)p * 6 + a);
         if (vb) for (int a = 0; a < 6; a++) x[a] += beta * ldc(vb + (size_t)p * 6 + a);
         if (zc) {
@@ -883,6 +1076,18 @@ struct Phase {
           const double* z1 = zc + (size_t)min(c0 + 1, G.nc - 1) * 6;
           for (int a = 0; a < 6; a++) x[a] += h0 * ldc(z0 + a) + h1 * ldc(z1 + a);
         }
+      }
+      if (c.use_tma) {
+        mbar_wait(bar + st, (c.tma_par >> st) & 1u);
+        c.tma_par ^= (1u << st);
+        if (key >= 0) {
+          const double* wt = buf + st * kWStride + lane;
+#pragma unroll
+          for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) u[b] += wt[(a * 3 + b) * 32] * x[a];
+        }
+      } else if (key >= 0) {
         const double* wt = G.Wt + (size_t)tile * kWStride + lane;
 #pragma unroll
         for (int a = 0; a < 6; a++)
@@ -895,6 +1100,7 @@ struct Phase {
         double* o = G.upart + (size_t)G.pl_part[s] * 3;
         o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
       }
+      __syncwarp();  // every lane is done with this stage before lane 0 refills it
     }
   }
 
@@ -963,6 +1169,8 @@ struct Phase {
     double* yp = reinterpret_cast<double*>(c.smem + kSmYp);
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
     const int lane = tid & 31, wis = u >> 5;  // warp within the slot (3 warps per slot)
+    double* tbuf = reinterpret_cast<double*>(c.smem + kSmTma) + (tid >> 5) * 2 * kWStride;  // TMA staging (large graphs)
+    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + (tid >> 5) * 2;
     double dot = 0;
     for (int rd = 0; rd < rounds(); rd++) {
       const int k = c.rank + c.tsize * (slot + kSlots * rd);
@@ -972,6 +1180,14 @@ struct Phase {
       const bool on = live && (p < G.N);
       __syncthreads();
       if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
+      if (live && c.use_tma && lane == 0) {
+        // first W tile of this warp: in flight while the plane-group vectors are formed
+        const int t0 = G.tile_ptr[k], nt = G.tile_ptr[k + 1] - t0;
+        if (wis < nt) {
+          fence_proxy_async();
+          tma_load_1d(tbuf, G.W + (size_t)(t0 + wis) * kWStride, kTileBytes, tbar);
+        }
+      }
       if (live) {
         // plane-group vectors: one thread per group when the plane has <= 8 partial sums (all loads in one
         // batch), one warp per group for heavy planes (the ground plane is seen from every pose)
@@ -1030,13 +1246,27 @@ struct Phase {
       if (!rhs) lap(21);
       if (live) {
         const int t0 = G.tile_ptr[k], nt = G.tile_ptr[k + 1] - t0, part0 = G.blk_part_ptr[k];
-        for (int t = wis; t < nt; t += 3) {
+        int st = 0;
+        for (int t = wis; t < nt; t += 3, st ^= 1) {
+          if (c.use_tma && lane == 0 && t + 3 < nt)
+            tma_load_1d(tbuf + (st ^ 1) * kWStride, G.W + (size_t)(t0 + t + 3) * kWStride, kTileBytes, tbar + (st ^ 1));
           const int e = (t0 + t) * 32 + lane;
           const int key = G.pp_pose[e];
           double y[6] = {0, 0, 0, 0, 0, 0};
+          double v0 = 0, v1 = 0, v2 = 0;
           if (key >= 0) {
             const double* v = vg + (slot * kMaxGrp + G.grp_of_slot[e]) * 3;
-            const double v0 = v[0], v1 = v[1], v2 = v[2];
+            v0 = v[0]; v1 = v[1]; v2 = v[2];
+          }
+          if (c.use_tma) {
+            mbar_wait(tbar + st, (c.tma_par >> st) & 1u);
+            c.tma_par ^= (1u << st);
+            if (key >= 0) {
+              const double* w = tbuf + st * kWStride + lane;
+#pragma unroll
+              for (int a = 0; a < 6; a++) y[a] = w[(a * 3) * 32] * v0 + w[(a * 3 + 1) * 32] * v1 + w[(a * 3 + 2) * 32] * v2;
+            }
+          } else if (key >= 0) {
             const double* w = G.W + (size_t)(t0 + t) * kWStride + lane;
 #pragma unroll
             for (int a = 0; a < 6; a++) y[a] = ldc(w + (a * 3) * 32) * v0 + ldc(w + (a * 3 + 1) * 32) * v1 + ldc(w + (a * 3 + 2) * 32) * v2;
@@ -1047,6 +1277,7 @@ struct Phase {
             double* o = yp + (slot * kMaxPart + (G.pm_part[e] - part0)) * 6;
             for (int a = 0; a < 6; a++) o[a] = y[a];
           }
+          __syncwarp();  // stage consumed by every lane before it is refilled
         }
       }
       __syncthreads();
@@ -1198,11 +1429,16 @@ struct Phase {
       const int nw = nwarp_team();
       for (int i = warp_team(); i < ldm; i += 2 * nw) {   // two rows per pass so both rows' loads are in flight
         const int i2 = i + nw;
-        const double* arow = Ai + (size_t)i * G.ldmc;
-        const double* brow = Ai + (size_t)min(i2, ldm - 1) * G.ldmc;
+        const double* arow = Ai + ac_index(G.ldmc, i, 0);
+        const double* brow = Ai + ac_index(G.ldmc, min(i2, ldm - 1), 0);
         double acc = 0, acc2 = 0;
 #pragma unroll 8
-        for (int j = lane; j < ldm; j += 32) { double sj = src[j]; acc += ldc(arow + j) * sj; acc2 += ldc(brow + j) * sj; }
+        for (int j = lane; j < ldm; j += 32) {
+          const double sj = src[j];
+          const size_t o = (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk);
+          acc += ldc(arow + o) * sj;
+          acc2 += ldc(brow + o) * sj;
+        }
         acc = warp_sum(acc);
         acc2 = warp_sum(acc2);
         if (lane == 0) {

@@ -68,6 +68,33 @@ def test_huber_corridor_trace_matches_oracle():
     compare(gpu, orc, ig, io)
 
 
+def test_tma_staged_tiles_match_direct_loads():
+    """the large-graph data path (W / Wt tiles staged through shared memory by cp.async.bulk + mbarrier, no block
+    cache) forced on a small Huber corridor: same trace and estimates as the default path and as the oracle."""
+    import ctypes
+    g = gg.make_config(3, seed=1, n_poses=700, n_planes=70, max_iterations=8)
+    orc = OracleAPI()
+    orc.set_jacobian_mode(1)
+    io = gg.build_bulk(orc, g)
+    gg.configure(orc, g)
+    it_o = orc.batch_optimize()
+    res = []
+    for flag in (0, 2):   # solver option reserved[2] bit 1: always stage tiles by TMA
+        gpu = GpuGraphAPI()
+        ig = gg.build_bulk(gpu, g)
+        gg.configure(gpu, g)
+        o = gpu.get_solver_options()
+        o.reserved[2] = flag
+        gpu._chk(gpu.lib.pus_set_solver_options(gpu.h, ctypes.byref(o)))
+        it_g = gpu.batch_optimize()
+        assert it_g == it_o
+        assert np.array_equal(gpu.trace()["accepted"], orc.trace()["accepted"])
+        compare(gpu, orc, ig, io)
+        res.append((gpu.chi2(), gpu.get_poses(ig["pose_ids"]), gpu.stats()["pcg_iterations"]))
+    assert abs(res[0][0] - res[1][0]) <= 1e-9 * abs(res[0][0])
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-9
+
+
 def test_gauss_newton_and_update_match_oracle():
     g = gg.make_config(2, seed=1)
     for which in ("gn", "update"):
