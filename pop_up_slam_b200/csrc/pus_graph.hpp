@@ -172,7 +172,7 @@ struct Compiled {
   std::vector<int> lp_fid, lp_plane, linc_ptr, linc;
   std::vector<double> lp_meas, lp_sinf;
   // dense-block groups: per pose block, its edges grouped by plane
-  std::vector<int> blk_grp_ptr, grp_plane, grp_mem_ptr, grp_mem;
+  std::vector<int> blk_grp_ptr, grp_plane, grp_mem_ptr, grp_mem, blk_simple;
   // coarse (hat) space: (plane, coarse node) pairs
   std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
 };
@@ -333,6 +333,7 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   }
   // ---- dense-block groups: the edges of every pose block grouped by plane ----
   c.blk_grp_ptr.assign(c.nblk + 1, 0);
+  c.blk_simple.assign(c.nblk, 0);
   c.grp_of_slot.assign(slots, 0);
   c.grp_mem_ptr.clear(); c.grp_mem.clear(); c.grp_plane.clear();
   for (int k = 0; k < c.nblk; k++) {
@@ -350,6 +351,12 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
       c.grp_mem.push_back(es[i]);
     }
     c.blk_grp_ptr[k + 1] = (int)c.grp_plane.size();
+    {  // fast dense-block build: at most 16 tiles, 96 planes and no pose observing one plane twice
+      bool simple = (c.tile_ptr[k + 1] - c.tile_ptr[k] <= 16) && ((int)c.grp_plane.size() - g0 <= 96);
+      for (int i = 1; i < (int)es.size() && simple; i++)
+        if (c.pp_plane[es[i]] == c.pp_plane[es[i - 1]] && c.pp_pose[es[i]] == c.pp_pose[es[i - 1]]) simple = false;
+      c.blk_simple[k] = simple ? 1 : 0;
+    }
     if (c.blk_grp_ptr[k + 1] - g0 > kMaxGrp || c.blk_part_ptr[k + 1] - c.blk_part_ptr[k] > kMaxPart) {
       err = "pose block " + std::to_string(k) + " observes too many planes (limits: " + std::to_string(kMaxGrp) +
             " distinct planes / " + std::to_string(kMaxPart) + " tile runs per 16 poses)";

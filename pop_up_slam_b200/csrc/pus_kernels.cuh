@@ -76,7 +76,7 @@ struct DevGraph {
   const int *lp_plane, *linc_ptr, *linc;
   const double *lp_meas, *lp_sinf;
   // dense-block groups, coarse pairs
-  const int *blk_grp_ptr, *grp_plane, *grp_mem_ptr, *grp_mem;
+  const int *blk_grp_ptr, *grp_plane, *grp_mem_ptr, *grp_mem, *blk_simple;
   const int *ce_ptr, *ce_node, *ce_plane, *ce_lo, *ce_hi, *n2ce_ptr, *n2ce;
   // work buffers
   double *W, *Wt, *JP, *JL, *PF, *LP;
@@ -212,12 +212,14 @@ constexpr int kSmRed = 0;                            // [kWarps][4] + [4] double
 constexpr int kSmRedBytes = (kWarps * 4 + 8) * 8;
 constexpr int kSmWork = 1024 + 64;                   // start of the phase-specific area
 // dense-block build: S0, S1 (96x96), Wg, Yg (kMaxStage x 18), P (36), Hinv (9)
+constexpr int kLdS = kBlockDim + 4;                  // padded row stride of the 96x96 block (conflict-free MMA fragments)
+constexpr int kFastTiles = 16, kFastGrp = 96;         // limits of the fast dense-block build (tiles / planes per block)
 constexpr int kSmS0 = kSmWork;
-constexpr int kSmS1 = kSmS0 + kBlockDim * kBlockDim * 8;
-constexpr int kSmWg = kSmS1 + kBlockDim * kBlockDim * 8;
+constexpr int kSmS1 = kSmS0 + kBlockDim * kLdS * 8;
+constexpr int kSmWg = kSmS1 + kBlockDim * kLdS * 8;  // slow path: staged group; fast path: (group, pose) -> slot table
 constexpr int kSmYg = kSmWg + kMaxStage * 18 * 8;
-constexpr int kSmP = kSmYg + kMaxStage * 18 * 8;
-constexpr int kSmHi = kSmP + 72 * 8;
+constexpr int kSmP = kSmYg + kMaxStage * 18 * 8;     // [96][12] coefficient columns of the inner inversion step
+constexpr int kSmHi = kSmP + kBlockDim * 12 * 8;
 constexpr int kSmBuildEnd = kSmHi + 16 * 8;
 // PCG phases: sA, sB [kSlots*96], szc [kSlots][12][8], rc [6*nc]
 constexpr int kSmA = kSmWork;
@@ -229,6 +231,8 @@ constexpr int kSmVg = kSmRc;
 constexpr int kSmYp = kSmVg + kSlots * kMaxGrp * 3 * 8;
 constexpr int kSmPoseEnd = kSmYp + kSlots * kMaxPart * 6 * 8;
 static_assert(kSmPoseEnd <= kSmBuildEnd, "shared-memory carve-up");
+static_assert(kFastTiles * 18 * 32 * 8 <= kBlockDim * kLdS * 8, "fast-build staging must fit the second block buffer");
+static_assert(kFastGrp * (16 * 2 + 9 * 8) <= 2 * kMaxStage * 18 * 8, "slot table + Hll^-1 must fit the group staging area");
 // PCG: packed-symmetric copies of the owned dense blocks (upper triangle, 4656 doubles each)
 constexpr int kPackedBlock = kBlockDim * (kBlockDim + 1) / 2;
 constexpr int kSmCache = 72 * 1024;                   // after the PCG work area (rc may use up to 72 KB - kSmRc)
@@ -381,6 +385,68 @@ struct Timer {
   }
   __device__ void flush(LmResult* res) { if (on) for (int i = 0; i < 24; i++) res->phase_ns[i] = acc[i]; }
 };
+
+// In-place style inversion of an n x n (n = 8 NB) SPD matrix held in shared memory with row stride LD, by
+// Gauss-Jordan with 8x8 inner blocks, ping-ponging between Mc and Mn (returns the buffer holding the inverse):
+// per inner step J every warp inverts the 8x8 diagonal block in registers (lane = column, shuffles, no block
+// sync), the threads form the coefficient columns TQ = -M[:,J] Q (+Q in the rows of J; these are also the pivot
+// columns of the result), and the rank-8 update of the remaining tiles runs on the FP64 tensor cores.
+// All threads of the CTA must call it; Mc must be complete (synchronised) on entry.
+template <int NB, int LD>
+__device__ __forceinline__ double* gj_invert_smem(double* Mc, double* Mn, double* TQ) {
+  constexpr int n = 8 * NB, LDQ = 12;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int fr = lane >> 2, fc = lane & 3, cidx = lane & 7;
+  for (int J = 0; J < NB; J++) {
+    double d[8];
+#pragma unroll
+    for (int a = 0; a < 8; a++) d[a] = Mc[(8 * J + a) * LD + 8 * J + cidx];
+#pragma unroll
+    for (int pp = 0; pp < 8; pp++) {
+      const double piv = fast_rcp(__shfl_sync(0xffffffffu, d[pp], pp));
+      double f[8];
+#pragma unroll
+      for (int a = 0; a < 8; a++) f[a] = __shfl_sync(0xffffffffu, d[a], pp);
+      const double rs = (cidx == pp) ? piv : d[pp] * piv;
+#pragma unroll
+      for (int a = 0; a < 8; a++)
+        if (a != pp) d[a] = (cidx == pp) ? -f[a] * piv : fma(-f[a], rs, d[a]);
+      d[pp] = rs;
+    }
+    // d[s] = Q[s][cidx];  entry (i, cidx) of TQ for i = tid/8, tid/8 + 64, ...
+    for (int i = tid >> 3; i < n; i += kThreads / 8) {
+      double v;
+      if (i >= 8 * J && i < 8 * J + 8) {
+        const int rr = i - 8 * J;
+        v = d[0];
+#pragma unroll
+        for (int a = 1; a < 8; a++) v = (rr == a) ? d[a] : v;
+      } else {
+        v = 0;
+#pragma unroll
+        for (int sx = 0; sx < 8; sx++) v = fma(-Mc[i * LD + 8 * J + sx], d[sx], v);
+      }
+      TQ[i * LDQ + cidx] = v;
+      Mn[i * LD + 8 * J + cidx] = v;
+    }
+    __syncthreads();
+    for (int u = warp; u < NB * (NB - 1); u += kWarps) {
+      const int mi = u / (NB - 1), nj = u - mi * (NB - 1), ni = nj + (nj >= J ? 1 : 0);
+      double cacc[2] = {0.0, 0.0};
+      if (mi != J) {
+        const double2 c2 = *reinterpret_cast<const double2*>(Mc + (8 * mi + fr) * LD + 8 * ni + 2 * fc);
+        cacc[0] = c2.x; cacc[1] = c2.y;
+      }
+#pragma unroll
+      for (int ks = 0; ks < 2; ks++)
+        dmma884(cacc, TQ[(8 * mi + fr) * LDQ + 4 * ks + fc], Mc[(8 * J + 4 * ks + fc) * LD + 8 * ni + fr]);
+      *reinterpret_cast<double2*>(Mn + (8 * mi + fr) * LD + 8 * ni + 2 * fc) = make_double2(cacc[0], cacc[1]);
+    }
+    __syncthreads();
+    double* t = Mc; Mc = Mn; Mn = t;
+  }
+  return Mc;
+}
 
 struct Phase {
   const DevGraph& G;
@@ -602,18 +668,19 @@ struct Phase {
 
   // -------- Schur setup, part 2: dense diagonal blocks of S, inverted in shared memory --------
   __device__ void build_blocks(double lambda) {
+    constexpr int LD = kLdS;
     double* S0 = reinterpret_cast<double*>(c.smem + kSmS0);
     double* S1 = reinterpret_cast<double*>(c.smem + kSmS1);
     double* Wg = reinterpret_cast<double*>(c.smem + kSmWg);
     double* Yg = reinterpret_cast<double*>(c.smem + kSmYg);
-    double* Ps = reinterpret_cast<double*>(c.smem + kSmP);
+    double* TQ = reinterpret_cast<double*>(c.smem + kSmP);
     double* His = reinterpret_cast<double*>(c.smem + kSmHi);
     const int tid = threadIdx.x;
     for (int k = c.rank; k < G.nblk; k += c.tsize) {
       const int p0 = k * kBlockPoses;
       const int np = min(kBlockPoses, G.N - p0);
       __syncthreads();
-      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) S0[i] = 0.0;
+      for (int i = tid; i < kBlockDim * LD; i += kThreads) S0[i] = 0.0;
       __syncthreads();
       // diagonal 6x6 blocks (damped) and identity padding
       for (int i = tid; i < kBlockPoses * 36; i += kThreads) {
@@ -625,7 +692,7 @@ struct Phase {
         } else {
           v = (a == b) ? 1.0 : 0.0;
         }
-        S0[(pi * 6 + a) * kBlockDim + pi * 6 + b] = v;
+        S0[(pi * 6 + a) * LD + pi * 6 + b] = v;
       }
       __syncthreads();
       // pose-pose factors with both ends inside the block (handled from side 0)
@@ -640,83 +707,119 @@ struct Phase {
           if (tid < 36) {
             int a = tid / 6, b = tid % 6;
             double v = ldc(G.PF + (size_t)f * 120 + 72 + tid);
-            S0[(pi * 6 + a) * kBlockDim + pj * 6 + b] += v;
-            S0[(pj * 6 + b) * kBlockDim + pi * 6 + a] += v;
+            S0[(pi * 6 + a) * LD + pj * 6 + b] += v;
+            S0[(pj * 6 + b) * LD + pi * 6 + a] += v;
           }
           __syncthreads();
         }
       }
-      // minus W Hll^-1 W^T restricted to the block, one plane group at a time
-      for (int g = G.blk_grp_ptr[k]; g < G.blk_grp_ptr[k + 1]; g++) {
-        const int m0 = G.grp_mem_ptr[g], m = G.grp_mem_ptr[g + 1] - m0;
-        const int l = G.grp_plane[g];
+      const int g0 = G.blk_grp_ptr[k], ng = G.blk_grp_ptr[k + 1] - g0;
+      if (G.blk_simple[k]) {
+        // fast path (no pose of the block observes a plane twice, <= kFastTiles tiles, <= kFastGrp planes): stage
+        // the block's W tiles in the second block buffer, the planes' Hll^-1 and a (group, pose) -> slot table;
+        // then every pose pair (pi, pj) is owned by two threads that walk the groups and accumulate their 6x6
+        // entries in registers -- no atomics, no per-group synchronisation, fixed summation order.
+        double* Wst = S1;
+        unsigned short* memb = reinterpret_cast<unsigned short*>(Wg);
+        double* Hst = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(Wg) + kFastGrp * 16 * 2);
+        const int t0 = G.tile_ptr[k], nt = G.tile_ptr[k + 1] - t0;
+        for (int i = tid; i < nt * kWStride; i += kThreads) Wst[i] = ldc(G.W + (size_t)t0 * kWStride + i);
+        for (int i = tid; i < ng * 8; i += kThreads) reinterpret_cast<unsigned*>(memb)[i] = 0xffffffffu;
+        for (int i = tid; i < ng * 9; i += kThreads) Hst[i] = ldc(G.Hinv + (size_t)G.grp_plane[g0 + i / 9] * 9 + i % 9);
         __syncthreads();
-        if (tid < 9) His[tid] = ldc(G.Hinv + (size_t)l * 9 + tid);
-        const bool staged = (m <= kMaxStage);
-        if (staged) {
-          for (int i = tid; i < m * 18; i += kThreads) {
-            int mi = i / 18, kk = i % 18;
-            int e = G.grp_mem[m0 + mi];
-            Wg[i] = ldc(G.W + (size_t)(e >> 5) * kWStride + kk * 32 + (e & 31));
-          }
-        }
-        __syncthreads();
-        if (staged) {
-          for (int i = tid; i < m * 18; i += kThreads) {
-            int mi = i / 18, kk = i % 18, a = kk / 3, b = kk % 3;
-            Yg[i] = Wg[mi * 18 + a * 3] * His[0 * 3 + b] + Wg[mi * 18 + a * 3 + 1] * His[1 * 3 + b] + Wg[mi * 18 + a * 3 + 2] * His[2 * 3 + b];
-          }
-        }
-        __syncthreads();
-        const int total = m * m * 36;
-        for (int idx = tid; idx < total; idx += kThreads) {
-          int mi = idx / (36 * m), rem = idx % (36 * m);
-          int mj = rem / 36, en = rem % 36, a = en / 6, b = en % 6;
-          int ei = G.grp_mem[m0 + mi], ej = G.grp_mem[m0 + mj];
-          int pi = G.pp_pose[ei] - p0, pj = G.pp_pose[ej] - p0;
-          double v;
-          if (staged) {
-            v = Yg[mi * 18 + a * 3] * Wg[mj * 18 + b * 3] + Yg[mi * 18 + a * 3 + 1] * Wg[mj * 18 + b * 3 + 1] +
-                Yg[mi * 18 + a * 3 + 2] * Wg[mj * 18 + b * 3 + 2];
-          } else {
-            double wi[3], wj[3];
-            for (int t = 0; t < 3; t++) {
-              wi[t] = ldc(G.W + (size_t)(ei >> 5) * kWStride + (a * 3 + t) * 32 + (ei & 31));
-              wj[t] = ldc(G.W + (size_t)(ej >> 5) * kWStride + (b * 3 + t) * 32 + (ej & 31));
-            }
-            v = 0;
-            for (int t = 0; t < 3; t++) {
-              double y = wi[0] * His[0 * 3 + t] + wi[1] * His[1 * 3 + t] + wi[2] * His[2 * 3 + t];
-              v += y * wj[t];
-            }
-          }
-          // distinct (mi,mj) pairs of one group hit distinct entries unless a pose observes the
-          // plane twice; the atomic keeps that (rare) case correct
-          atomicAdd(&S0[(pi * 6 + a) * kBlockDim + pj * 6 + b], -v);
-        }
-      }
-      __syncthreads();
-      // blocked Gauss-Jordan inversion in shared memory (ping-pong S0 <-> S1)
-      double* src = S0;
-      double* dst = S1;
-      for (int kk = 0; kk < kBlockPoses; kk++) {
-        if (tid == 0) {
-          double A[36], Pi[36];
-          for (int e = 0; e < 36; e++) A[e] = src[(kk * 6 + e / 6) * kBlockDim + kk * 6 + e % 6];
-          inv6(A, Pi);
-          for (int e = 0; e < 36; e++) Ps[e] = Pi[e];
+        for (int sl = tid; sl < nt * 32; sl += kThreads) {
+          const int e = t0 * 32 + sl, p = G.pp_pose[e];
+          if (p >= 0) memb[G.grp_of_slot[e] * 16 + (p - p0)] = (unsigned short)sl;
         }
         __syncthreads();
         {
-          const double* sp = src;
-          for (int idx = tid; idx < kBlockDim * kBlockDim; idx += kThreads)
-            dst[idx] = gj_entry([sp](int off) { return sp[off]; }, kBlockDim, idx / kBlockDim, idx % kBlockDim, kk, Ps);
+          const int pair = tid >> 1, half = tid & 1, pi = pair >> 4, pj = pair & 15;
+          double acc[3][6];
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 6; b++) acc[a][b] = 0.0;
+          for (int g = 0; g < ng; g++) {
+            const int si = memb[g * 16 + pi], sj = memb[g * 16 + pj];
+            if (si == 0xffff || sj == 0xffff) continue;
+            const double* wi = Wst + (si >> 5) * kWStride + (si & 31) + (half * 9) * 32;
+            const double* wj = Wst + (sj >> 5) * kWStride + (sj & 31);
+            const double* Hi = Hst + g * 9;
+            double yv[3][3];   // rows 3*half .. 3*half+2 of  W_i Hll^-1
+#pragma unroll
+            for (int a = 0; a < 3; a++) {
+              const double w0 = wi[(a * 3) * 32], w1 = wi[(a * 3 + 1) * 32], w2 = wi[(a * 3 + 2) * 32];
+#pragma unroll
+              for (int t = 0; t < 3; t++) yv[a][t] = w0 * Hi[t] + w1 * Hi[3 + t] + w2 * Hi[6 + t];
+            }
+#pragma unroll
+            for (int b = 0; b < 6; b++) {
+              const double w0 = wj[(b * 3) * 32], w1 = wj[(b * 3 + 1) * 32], w2 = wj[(b * 3 + 2) * 32];
+#pragma unroll
+              for (int a = 0; a < 3; a++) acc[a][b] += yv[a][0] * w0 + yv[a][1] * w1 + yv[a][2] * w2;
+            }
+          }
+#pragma unroll
+          for (int a = 0; a < 3; a++)
+#pragma unroll
+            for (int b = 0; b < 6; b++) S0[(pi * 6 + half * 3 + a) * LD + pj * 6 + b] -= acc[a][b];
         }
-        __syncthreads();
-        double* t = src; src = dst; dst = t;
+      } else {
+        // general path: minus W Hll^-1 W^T restricted to the block, one plane group at a time
+        for (int g = g0; g < g0 + ng; g++) {
+          const int m0 = G.grp_mem_ptr[g], m = G.grp_mem_ptr[g + 1] - m0;
+          const int l = G.grp_plane[g];
+          __syncthreads();
+          if (tid < 9) His[tid] = ldc(G.Hinv + (size_t)l * 9 + tid);
+          const bool staged = (m <= kMaxStage);
+          if (staged) {
+            for (int i = tid; i < m * 18; i += kThreads) {
+              int mi = i / 18, kk = i % 18;
+              int e = G.grp_mem[m0 + mi];
+              Wg[i] = ldc(G.W + (size_t)(e >> 5) * kWStride + kk * 32 + (e & 31));
+            }
+          }
+          __syncthreads();
+          if (staged) {
+            for (int i = tid; i < m * 18; i += kThreads) {
+              int mi = i / 18, kk = i % 18, a = kk / 3, b = kk % 3;
+              Yg[i] = Wg[mi * 18 + a * 3] * His[0 * 3 + b] + Wg[mi * 18 + a * 3 + 1] * His[1 * 3 + b] + Wg[mi * 18 + a * 3 + 2] * His[2 * 3 + b];
+            }
+          }
+          __syncthreads();
+          const int total = m * m * 36;
+          for (int idx = tid; idx < total; idx += kThreads) {
+            int mi = idx / (36 * m), rem = idx % (36 * m);
+            int mj = rem / 36, en = rem % 36, a = en / 6, b = en % 6;
+            int ei = G.grp_mem[m0 + mi], ej = G.grp_mem[m0 + mj];
+            int pi = G.pp_pose[ei] - p0, pj = G.pp_pose[ej] - p0;
+            double v;
+            if (staged) {
+              v = Yg[mi * 18 + a * 3] * Wg[mj * 18 + b * 3] + Yg[mi * 18 + a * 3 + 1] * Wg[mj * 18 + b * 3 + 1] +
+                  Yg[mi * 18 + a * 3 + 2] * Wg[mj * 18 + b * 3 + 2];
+            } else {
+              double wi[3], wj[3];
+              for (int t = 0; t < 3; t++) {
+                wi[t] = ldc(G.W + (size_t)(ei >> 5) * kWStride + (a * 3 + t) * 32 + (ei & 31));
+                wj[t] = ldc(G.W + (size_t)(ej >> 5) * kWStride + (b * 3 + t) * 32 + (ej & 31));
+              }
+              v = 0;
+              for (int t = 0; t < 3; t++) {
+                double y = wi[0] * His[0 * 3 + t] + wi[1] * His[1 * 3 + t] + wi[2] * His[2 * 3 + t];
+                v += y * wj[t];
+              }
+            }
+            // distinct (mi,mj) pairs of one group hit distinct entries unless a pose observes the
+            // plane twice; the atomic keeps that (rare) case correct
+            atomicAdd(&S0[(pi * 6 + a) * LD + pj * 6 + b], -v);
+          }
+        }
       }
+      __syncthreads();
+      // inversion in shared memory (S0 <-> S1), then the dense copy for the PCG
+      const double* inv = gj_invert_smem<kBlockDim / 8, LD>(S0, S1, TQ);
       double* out = G.Binv + (size_t)k * kBlockDim * kBlockDim;
-      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) out[i] = src[i];
+      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) out[i] = inv[(i / kBlockDim) * LD + i % kBlockDim];
     }
     __syncthreads();
   }
@@ -857,65 +960,8 @@ struct Phase {
       for (int i = tid; i < band * PW; i += kThreads) Ab[i] = ldc(src + ac_index(ldm, r0 + i / PW, k0 + i % PW));
       __syncthreads();
       lap(6);
-      // Inversion of the 48x48 pivot block (SPD: no pivoting) by Gauss-Jordan with 8x8 inner blocks.  Per inner
-      // step J: every warp inverts the 8x8 diagonal block in registers (lane = column, shuffles, no block sync),
-      // the first 384 threads form the coefficient columns TQ = -M[:,J] Q (+Q in the rows of J), and the rank-8
-      // update of the other 30 tiles runs on the FP64 tensor cores from one buffer into the other.
-      {
-        double* Mc = Pa;
-        double* Mn = Pb;
-        const int cidx = lane & 7;
-        for (int J = 0; J < PW / 8; J++) {
-          double d[8];
-#pragma unroll
-          for (int a = 0; a < 8; a++) d[a] = Mc[(8 * J + a) * LDP + 8 * J + cidx];
-#pragma unroll
-          for (int pp = 0; pp < 8; pp++) {
-            const double piv = fast_rcp(__shfl_sync(0xffffffffu, d[pp], pp));
-            double f[8];
-#pragma unroll
-            for (int a = 0; a < 8; a++) f[a] = __shfl_sync(0xffffffffu, d[a], pp);
-            const double rs = (cidx == pp) ? piv : d[pp] * piv;
-#pragma unroll
-            for (int a = 0; a < 8; a++)
-              if (a != pp) d[a] = (cidx == pp) ? -f[a] * piv : fma(-f[a], rs, d[a]);
-            d[pp] = rs;
-          }
-          // d[s] = Q[s][cidx]
-          if (tid < PW * 8) {
-            const int i = tid >> 3;   // row of the 48x48 block; column t of TQ is cidx
-            double v;
-            if (i >= 8 * J && i < 8 * J + 8) {
-              const int rr = i - 8 * J;
-              v = d[0];
-#pragma unroll
-              for (int a = 1; a < 8; a++) v = (rr == a) ? d[a] : v;
-            } else {
-              v = 0;
-#pragma unroll
-              for (int sx = 0; sx < 8; sx++) v = fma(-Mc[i * LDP + 8 * J + sx], d[sx], v);
-            }
-            TQ[i * LDQ + cidx] = v;
-            Mn[i * LDP + 8 * J + cidx] = v;   // the pivot columns of the result are TQ itself
-          }
-          __syncthreads();
-          for (int u = warp; u < 30; u += kWarps) {
-            const int mi = u / 5, nj = u - mi * 5, ni = nj + (nj >= J ? 1 : 0);
-            double cacc[2] = {0.0, 0.0};
-            if (mi != J) {
-              const double2 c2 = *reinterpret_cast<const double2*>(Mc + (8 * mi + fr) * LDP + 8 * ni + 2 * fc);
-              cacc[0] = c2.x; cacc[1] = c2.y;
-            }
-#pragma unroll
-            for (int ks = 0; ks < 2; ks++)
-              dmma884(cacc, TQ[(8 * mi + fr) * LDQ + 4 * ks + fc], Mc[(8 * J + 4 * ks + fc) * LDP + 8 * ni + fr]);
-            *reinterpret_cast<double2*>(Mn + (8 * mi + fr) * LDP + 8 * ni + 2 * fc) = make_double2(cacc[0], cacc[1]);
-          }
-          __syncthreads();
-          double* t = Mc; Mc = Mn; Mn = t;
-        }
-      }
-      const double* Pm = Pa;  // six inner steps: the result is back in the first buffer
+      // inversion of the 48x48 pivot block (SPD: no pivoting), see gj_invert_smem()
+      const double* Pm = gj_invert_smem<PW / 8, LDP>(Pa, Pb, TQ);
       lap(7);
       // coefficient rows (negated): Tn = -(A[band,K] * P) for ordinary rows, +P for the rows of the pivot block
       // itself, so that every entry outside the pivot columns is  base + sum_t Tn[row][t] * A[K][col]
