@@ -274,7 +274,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": tot_ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD, **dims, "lm_iterations_per_solve": iters_res[-1], "accepted": st["accepted"],
-                   "pcg_iterations_per_solve": st["pcg_iterations"], "pcg_rel_tol": 1e-10, "seed": 0,
+                   "pcg_iterations_per_solve": st["pcg_iterations"], "pcg_rel_tol": api.get_solver_options().pcg_rel_tol, "seed": 0,
                    "properties": g.properties, "robust": {"kind": "huber", "b": g.robust_b},
                    "l2_flush": "256 MiB device write before every timed step (outside the per-step CUDA-event pair)",
                    "replicas": "one graph per rank, no data-path collective"},

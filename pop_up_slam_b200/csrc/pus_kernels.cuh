@@ -1031,10 +1031,8 @@ struct Phase {
         if (ci + 1 < nchunk) issue(ci + 1);
         double acc[2][2] = {{cn[0][0], cn[0][1]}, {cn[1][0], cn[1][1]}};
         if (ci + 1 < nchunk) loadC0(ci + 1, cn);
-        lap(16);
         mbar_wait(gbar + (ci & 1), (c.gj_par >> (ci & 1)) & 1u);
         c.gj_par ^= (1u << (ci & 1));
-        lap(17);
         const double* buf = Rc + (ci & 1) * PW * LDR;
         const int col = ci * CW + 8 * warp + 2 * fc;
         const bool nlive = (ci * CW + 8 * warp < ldm);
@@ -1074,9 +1072,7 @@ struct Phase {
             }
           }
         }
-        lap(18);
         __syncthreads();   // the buffer is free for chunk ci + 2
-        lap(19);
       }
       fence_proxy_async();  // the other CTAs' bulk copies read these rows in the next step
       lap(22);

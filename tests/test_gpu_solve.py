@@ -95,6 +95,28 @@ def test_tma_staged_tiles_match_direct_loads():
     assert np.abs(res[0][1] - res[1][1]).max() <= 1e-9
 
 
+def test_repeated_observations_of_one_plane():
+    """a pose that observes the same plane twice (the reference allows it: Mapping.cpp adds a factor per matched
+    segment) takes the general dense-block build path instead of the pose-pair fast path; same answer as the oracle."""
+    g = gg.make_config(2, seed=4, n_poses=60, n_planes=15)
+    rng = np.random.default_rng(0)
+    dup = rng.choice(len(g.pp_pose), size=25, replace=False)
+    gpu, orc = GpuGraphAPI(), OracleAPI()
+    orc.set_jacobian_mode(1)
+    ids = []
+    for api in (gpu, orc):
+        info = gg.build_bulk(api, g)
+        for e in dup:
+            m = g.pp_meas[e].copy()
+            m[3] += 0.01     # a slightly different second measurement of the same plane from the same pose
+            api.add_pose_plane(int(info["pose_ids"][g.pp_pose[e]]), int(info["plane_ids"][g.pp_plane[e]]), m / np.linalg.norm(m), g.pp_sqrtinf[e])
+        gg.configure(api, g)
+        ids.append(info)
+    assert gpu.batch_optimize() == orc.batch_optimize()
+    assert np.array_equal(gpu.trace()["accepted"], orc.trace()["accepted"])
+    compare(gpu, orc, ids[0], ids[1])
+
+
 def test_gauss_newton_and_update_match_oracle():
     g = gg.make_config(2, seed=1)
     for which in ("gn", "update"):

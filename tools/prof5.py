@@ -10,4 +10,3 @@ a.upload(); a.debug_run_stage(1, 1e-6)
 st = a.stats(); ph = st['phase_ms']
 print("one setup: Hinv %.3f blocks %.3f Wc %.3f Ac %.3f AcInv %.3f ms"%(ph[8],ph[9],ph[10],ph[11],ph[12]))
 print(" AcInv parts (40 steps): load %.1f  pivot-inv %.1f  T %.1f  chunks %.1f  barrier %.1f us/step"%tuple(ph[k]*1e3/40 for k in (6,7,21,22,23)))
-print(" chunk parts (us/step): issue+Cload %.1f  wait %.1f  mma+store %.1f  sync %.1f"%tuple(ph[k]*1e3/40 for k in (16,17,18,19)))
