@@ -1424,6 +1424,29 @@ struct Phase {
     const int bpn = G.SP / kBlockPoses;  // blocks per coarse interval
     // full coarse residual rc = sum_k rc_old[k] - alpha * sum_k qcpart[k]  (linear in r)
     __syncthreads();
+    if (bpn == 1) {
+      // one block per coarse interval (graphs up to 5120 poses): block `node` feeds the node through its slot 0,
+      // block `node-1` through slot 1; four outputs per thread so that all 16 loads are in flight together
+      for (int i0 = tid; i0 < ldm; i0 += 4 * kThreads) {
+        double va[4][2], vq[4][2];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const int i = i0 + m * kThreads, node = i / 6, row = i - node * 6;
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            const int k = node - side;
+            const bool ok = (i < ldm) && (k >= 0) && (k < G.nblk);
+            va[m][side] = ok ? ldc(rc_old + (size_t)k * 12 + side * 6 + row) : 0.0;
+            vq[m][side] = (ok && !first) ? ldc(G.qcpart + (size_t)k * 12 + side * 6 + row) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const int i = i0 + m * kThreads;
+          if (i < ldm) src[i] = (0.0 + (va[m][0] - alpha * vq[m][0])) + (va[m][1] - alpha * vq[m][1]);
+        }
+      }
+    } else
     for (int i = tid; i < ldm; i += kThreads) {
       int node = i / 6, row = i % 6;
       // blocks with c0 == node feed `node` through their slot 0, blocks with c0 == node-1 through slot 1;
@@ -1469,24 +1492,23 @@ struct Phase {
     {
       const int lane = tid & 31;
       const int nw = nwarp_team();
-      for (int i = warp_team(); i < ldm; i += 2 * nw) {   // two rows per pass so both rows' loads are in flight
-        const int i2 = i + nw;
+      for (int i = warp_team(); i < ldm; i += nw) {
         const double* arow = Ai + ac_index(G.ldmc, i, 0);
-        const double* brow = Ai + ac_index(G.ldmc, min(i2, ldm - 1), 0);
-        double acc = 0, acc2 = 0;
-#pragma unroll 8
-        for (int j = lane; j < ldm; j += 32) {
-          const double sj = src[j];
-          const size_t o = (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk);
-          acc += ldc(arow + o) * sj;
-          acc2 += ldc(brow + o) * sj;
+        double acc = 0;
+        int j = lane;
+        for (; j + 32 * 15 < ldm; j += 32 * 16) {   // 16 loads per lane in flight
+          double av[16];
+#pragma unroll
+          for (int t = 0; t < 16; t++) {
+            const int jj = j + 32 * t;
+            av[t] = ldc(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk));
+          }
+#pragma unroll
+          for (int t = 0; t < 16; t++) acc += av[t] * src[j + 32 * t];
         }
+        for (; j < ldm; j += 32) acc += ldc(arow + (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk)) * src[j];
         acc = warp_sum(acc);
-        acc2 = warp_sum(acc2);
-        if (lane == 0) {
-          G.zc[i] = acc; dot += src[i] * acc;
-          if (i2 < ldm) { G.zc[i2] = acc2; dot += src[i2] * acc2; }
-        }
+        if (lane == 0) { G.zc[i] = acc; dot += src[i] * acc; }
       }
     }
     lap(14);
