@@ -72,6 +72,7 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
     // one pseudo-iteration with direction p = x_prev and step 1:  x = x_prev, r = b - S x_prev, z = M^-1 r
     ph.sweep_planes(G.xprev, nullptr, 0.0);
     team_barrier(c);
+    if (c.use_tma) { ph.solve_heavy(); team_barrier(c); }
     ph.pose_phase(false, G.xprev, lambda, G.q, G.qcpart);
     team_barrier(c);
     v[0] = ph.precondition(1.0, G.xprev, acinv, G.rcpart[rcb], G.rcpart[rcb ^ 1], false);
@@ -86,6 +87,7 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
       ph.update_direction(cur, beta);
       ph.sweep_planes(G.z, G.pv[cur], beta, G.zc);
       team_barrier(c);
+      if (c.use_tma) { ph.solve_heavy(); team_barrier(c); }
       ft.lap(16);
       v[0] = ph.pose_phase(false, G.pv[cur ^ 1], lambda, G.q, G.qcpart);
       team_reduce<1>(c, G.red, v);
@@ -139,6 +141,7 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
     if (P.debug_stage == 3) {  // q = S * pv[0] with the current linearisation / Schur set-up
       ph.sweep_planes(G.pv[0], nullptr, 0.0);
       team_barrier(c);
+      if (c.use_tma) { ph.solve_heavy(); team_barrier(c); }
       ph.pose_phase(false, G.pv[0], P.debug_lambda, G.q, nullptr);
       team_barrier(c);
       return;
@@ -448,11 +451,14 @@ static int upload(Solver* s) {
 #define UP(field) if (s->dupload(&d.field, c.field, &bytes) < 0) return -1
     UP(pp_pose); UP(pp_plane); UP(pp_ptr); UP(pp_end); UP(pm2pl); UP(pm_part); UP(ypart_ptr); UP(tile_ptr); UP(blk_part_ptr);
     UP(grp_of_slot); UP(pp_meas); UP(pp_sinf);
-    UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr);
+    UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr); UP(heavy);
+    d.n_heavy = (int)c.heavy.size();
     UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pf_meas); UP(pf_sinf);
     UP(lp_plane); UP(linc_ptr); UP(linc); UP(lp_meas); UP(lp_sinf);
     UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple);
     UP(ce_ptr); UP(ce_node); UP(ce_plane); UP(ce_lo); UP(ce_hi); UP(n2ce_ptr); UP(n2ce);
+    UP(hv_plane); UP(lp_ptr); UP(lp_cea); UP(lp_ceb); UP(fp_ptr); UP(fp_f);
+    d.n_hv = c.n_hv;
 #undef UP
     const size_t N = c.N, M = c.M, E = c.nslot, T = c.ntile, TL = c.ntile_pl;
 #define AL(field, n, name) if (s->dalloc(&d.field, (size_t)(n), name) < 0) return -1
@@ -462,7 +468,7 @@ static int upload(Solver* s) {
     AL(PF, (size_t)c.Epf * 120, "PF"); AL(LP, (size_t)c.Elp * 12, "LP");
     AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
     AL(vl, M * 3, "vl"); AL(dl, M * 3, "dl"); AL(upart, (size_t)c.n_upart * 3, "upart"); AL(ypart, 8, "ypart");
-    AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc");
+    AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc"); AL(Yc, (size_t)c.nce * 18, "Yc");
     AL(Ac[0], ac_doubles(6 * c.nc_pad), "Ac0"); AL(Ac[1], ac_doubles(6 * c.nc_pad), "Ac1");
     AL(x, N * 6, "x"); AL(r, N * 6, "r"); AL(z, N * 6, "z"); AL(q, N * 6, "q"); AL(b, N * 6, "b");
     AL(pv[0], N * 6, "pv0"); AL(pv[1], N * 6, "pv1"); AL(xprev, N * 6, "xprev"); AL(zc, (size_t)6 * c.nc, "zc");

@@ -26,6 +26,7 @@ constexpr int kBlockPoses = 16;            // poses per dense preconditioner blo
 constexpr int kBlockDim = 6 * kBlockPoses; // 96
 constexpr int kCoarseSpacing = 16;         // base spacing (poses) of the coarse hat-function nodes; multiple of kBlockPoses
 constexpr int kMaxCoarseNodes = 320;       // the spacing grows in steps of 16 so that the dense A_c stays <= 1920^2
+constexpr int kHeavyCoarse = 16;           // planes touching more coarse nodes than this are dense rank-3 updates of A_c
 constexpr int kPivotNodes = 8;             // coarse nodes per pivot block of the blocked Gauss-Jordan inversion (48 scalars)
 constexpr int kTile = 32;                  // edges per warp tile
 constexpr int kWStride = 18 * kTile;       // doubles per W tile
@@ -154,7 +155,7 @@ struct Compiled {
   int N = 0, M = 0, Epl = 0, Epf = 0, Elp = 0;
   int SP = kCoarseSpacing;
   int nc_pad = 0;  // nc rounded up to whole pivot blocks; the padding nodes carry identity blocks
-  int ntile = 0, nslot = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0;
+  int ntile = 0, nslot = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0, n_hv = 0;
   std::vector<int> pose_node, plane_node;   // idx -> node id
   std::vector<int> node_idx;                // node id -> idx (pose idx or plane idx), -1 dead
   std::vector<double> pose_val, plane_val;  // [N*7], [M*4]
@@ -163,7 +164,7 @@ struct Compiled {
   std::vector<int> pp_fid, pp_pose, pp_plane, pp_ptr, pm2pl, pm_part, ypart_ptr, tile_ptr, blk_part_ptr, grp_of_slot;
   std::vector<double> pp_meas, pp_sinf;
   // plane-major view
-  std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr, pp_end;
+  std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr, pp_end, heavy;
   int ntile_pl = 0;
   // pose factors (prior / odometry)
   std::vector<int> pf_fid, pf_i, pf_j, pinc_ptr, pinc;
@@ -175,6 +176,7 @@ struct Compiled {
   std::vector<int> blk_grp_ptr, grp_plane, grp_mem_ptr, grp_mem, blk_simple;
   // coarse (hat) space: (plane, coarse node) pairs
   std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
+  std::vector<int> hv_plane, lp_ptr, lp_cea, lp_ceb, fp_ptr, fp_f;   // coarse assembly: heavy planes, per node-pair lists
 };
 
 inline int coarse_spacing(int N) { return kCoarseSpacing * std::max(1, (N + kCoarseSpacing * kMaxCoarseNodes - 1) / (kCoarseSpacing * kMaxCoarseNodes)); }
@@ -310,6 +312,9 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     }
     c.n_upart = np;
     for (int l = 0; l < M; l++) { c.pl_ptr[l + 1] += c.pl_ptr[l]; c.upart_ptr[l + 1] += c.upart_ptr[l]; }
+    c.heavy.clear();   // planes with more than 8 partial sums (summed by a warp; once per iteration on large graphs)
+    for (int l = 0; l < M; l++) if (c.upart_ptr[l + 1] - c.upart_ptr[l] > 8) c.heavy.push_back(l);
+    if (c.heavy.empty()) c.heavy.push_back(-1);
   }
   // ---- incidence lists ----
   c.pinc_ptr.assign(N + 1, 0);
@@ -402,6 +407,68 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   {
     std::vector<int> fill(c.n2ce_ptr.begin(), c.n2ce_ptr.end() - 1);
     for (int i = 0; i < c.nce; i++) c.n2ce[fill[c.ce_node[i]]++] = i;
+  }
+  // ---- output-stationary assembly of A_c = P^T S P: for every coarse node pair (a, b) the plane products
+  // Wc[a,l] Hll^-1 Wc[b,l]^T of the light planes and the pose-pose factors coupling the two supports; planes that
+  // touch more than kHeavyCoarse nodes (the ground plane touches all) are applied as dense rank-3 updates instead
+  {
+    const int nc = c.nc;
+    const size_t np = (size_t)nc * nc;
+    c.hv_plane.clear();
+    std::vector<char> heavy(M, 0);
+    for (int l = 0; l < M; l++)
+      if (c.ce_ptr[l + 1] - c.ce_ptr[l] > kHeavyCoarse) { heavy[l] = 1; c.hv_plane.push_back(l); }
+    c.n_hv = (int)c.hv_plane.size();
+    if (c.hv_plane.empty()) c.hv_plane.push_back(-1);
+    c.lp_ptr.assign(np + 1, 0);
+    for (int l = 0; l < M; l++) {
+      if (heavy[l]) continue;
+      for (int i = c.ce_ptr[l]; i < c.ce_ptr[l + 1]; i++)
+        for (int j = c.ce_ptr[l]; j < c.ce_ptr[l + 1]; j++) c.lp_ptr[(size_t)c.ce_node[i] * nc + c.ce_node[j] + 1]++;
+    }
+    for (size_t q = 0; q < np; q++) c.lp_ptr[q + 1] += c.lp_ptr[q];
+    c.lp_cea.assign(std::max(1, c.lp_ptr[np]), 0);
+    c.lp_ceb.assign(std::max(1, c.lp_ptr[np]), 0);
+    {
+      std::vector<int> fill(c.lp_ptr.begin(), c.lp_ptr.end() - 1);
+      for (int l = 0; l < M; l++) {   // plane-ascending order inside every pair: fixed summation order
+        if (heavy[l]) continue;
+        for (int i = c.ce_ptr[l]; i < c.ce_ptr[l + 1]; i++)
+          for (int j = c.ce_ptr[l]; j < c.ce_ptr[l + 1]; j++) {
+            int at = fill[(size_t)c.ce_node[i] * nc + c.ce_node[j]]++;
+            c.lp_cea[at] = i; c.lp_ceb[at] = j;
+          }
+      }
+    }
+    auto nodes_of = [&](int p, int* out) {   // coarse nodes whose hat function is non-zero at pose p
+      int n = 0, c0 = p / SPc;
+      if (c0 < nc) out[n++] = c0;
+      if ((p % SPc) && c0 + 1 < nc) out[n++] = c0 + 1;
+      return n;
+    };
+    c.fp_ptr.assign(np + 1, 0);
+    for (int pass = 0; pass < 2; pass++) {
+      std::vector<int> fill;
+      if (pass == 1) {
+        for (size_t q = 0; q < np; q++) c.fp_ptr[q + 1] += c.fp_ptr[q];
+        c.fp_f.assign(std::max(1, c.fp_ptr[np]), 0);
+        fill.assign(c.fp_ptr.begin(), c.fp_ptr.end() - 1);
+      }
+      for (int f = 0; f < c.Epf; f++) {
+        if (c.pf_j[f] < 0) continue;
+        for (int side = 0; side < 2; side++) {
+          const int p = side ? c.pf_j[f] : c.pf_i[f], o = side ? c.pf_i[f] : c.pf_j[f];
+          int na[2], nb[2];
+          const int ka = nodes_of(p, na), kb = nodes_of(o, nb);
+          for (int x = 0; x < ka; x++)
+            for (int y = 0; y < kb; y++) {
+              const size_t q = (size_t)na[x] * nc + nb[y];
+              if (pass == 0) c.fp_ptr[q + 1]++;
+              else c.fp_f[fill[q]++] = f * 2 + side;
+            }
+        }
+      }
+    }
   }
   return true;
 }

@@ -69,7 +69,8 @@ struct DevGraph {
   // pose-plane edges (pose-major) and plane-major view
   const int *pp_pose, *pp_plane, *pp_ptr, *pp_end, *pm2pl, *pm_part, *ypart_ptr, *tile_ptr, *blk_part_ptr, *grp_of_slot;
   const double *pp_meas, *pp_sinf;
-  const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr;
+  const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr, *heavy;
+  int n_heavy;
   // pose factors / plane priors
   const int *pf_i, *pf_j, *pinc_ptr, *pinc;
   const double *pf_meas, *pf_sinf;
@@ -78,11 +79,13 @@ struct DevGraph {
   // dense-block groups, coarse pairs
   const int *blk_grp_ptr, *grp_plane, *grp_mem_ptr, *grp_mem, *blk_simple;
   const int *ce_ptr, *ce_node, *ce_plane, *ce_lo, *ce_hi, *n2ce_ptr, *n2ce;
+  const int *hv_plane, *lp_ptr, *lp_cea, *lp_ceb, *fp_ptr, *fp_f;
+  int n_hv;
   // work buffers
   double *W, *Wt, *JP, *JL, *PF, *LP;
   double *Hpp, *gp, *Hll, *gl, *Hinv, *vl, *dl;
   double *upart, *ypart;
-  double *Binv, *Wc, *Ac[2];
+  double *Binv, *Wc, *Yc, *Ac[2];
   double *x, *r, *z, *q, *b, *pv[2], *xprev, *zc;
   double *rcpart[2], *qcpart;
   double *red;
@@ -848,81 +851,87 @@ struct Phase {
 #pragma unroll
         for (int k = 1; k < 18; k++) if (lane == k) v = acc[k];
         G.Wc[(size_t)ce * 18 + lane] = v;
+        // Yc = Wc * Hll_d^-1 (6x3), entry (r, b) = lane
+        const int r = lane / 3, b = lane - r * 3;
+        const double* Hi = G.Hinv + (size_t)G.ce_plane[ce] * 9;
+        double y = 0;
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+          double w = acc[0];
+#pragma unroll
+          for (int q = 1; q < 18; q++) if (r * 3 + k == q) w = acc[q];
+          y += w * ldc(Hi + k * 3 + b);
+        }
+        G.Yc[(size_t)ce * 18 + lane] = y;
       }
     }
   }
 
   // -------- Schur setup, part 4: A_c = P^T S P, one warp per coarse row panel --------
+  // Output-stationary: every thread owns entries (i, j) of A_c = P^T S P and writes each exactly once
+  // (coalesced along j, tiled layout):  pose part (supports of the two nodes overlap: |a-b| <= 1), pose-pose factors
+  // coupling the supports (host-built per-pair list), light planes (host-built per-pair list of (Yc, Wc) products),
+  // heavy planes (Yc / Wc rows of the plane staged per node in shared memory: dense rank-3 update, one pass each).
   __device__ void coarse_assemble(double lambda) {
-    const int lane = threadIdx.x & 31;
-    const int ldm = G.ldmc;
+    const int ldm = G.ldmc, nc = G.nc, n6 = 6 * nc;
     double* A = G.Ac[0];
-    for (int a = warp_team(); a < ldm / 6; a += nwarp_team()) {
-      for (int i = lane; i < 6 * ldm; i += 32) A[ac_index(ldm, a * 6 + i / ldm, i % ldm)] = 0.0;
-      __syncwarp();
-      if (a >= G.nc) {  // padding node: identity block
-        if (lane < 6) A[ac_index(ldm, a * 6 + lane, a * 6 + lane)] = 1.0;
-        continue;
-      }
-      // P^T Hpp_d P and pose-pose off-diagonals
-      int plo = max(0, (a - 1) * G.SP + 1), phi = min(G.N, (a + 1) * G.SP);
-      for (int p = plo; p < phi; p++) {
-        double ha = hat(p, a);
-        int c0 = p / G.SP;
-        for (int q = 0; q < 2; q++) {
-          int bnode = c0 + q;
-          if (bnode >= G.nc) continue;
-          double hb = hat(p, bnode);
-          if (hb == 0.0) continue;
-          for (int en = lane; en < 36; en += 32) {
-            int r = en / 6, cc = en % 6;
-            double v = ldc(G.Hpp + (size_t)p * 36 + en);
-            if (r == cc) v *= (1 + lambda);
-            { double* dstp = &A[ac_index(ldm, a * 6 + r, bnode * 6 + cc)]; *dstp = ldc(dstp) + (ha * hb * v); }
-          }
+    double* Yh = reinterpret_cast<double*>(c.smem + kSmWork);   // [nc][18]
+    double* Wh = Yh + (size_t)nc * 18;                          // [nc][18]
+    const int npass = max(1, G.n_hv);
+    const long long total = (long long)ldm * ldm;
+    for (int pass = 0; pass < npass; pass++) {
+      if (G.n_hv > 0) {
+        __syncthreads();
+        for (int i = threadIdx.x; i < nc * 36; i += kThreads) Yh[i] = 0.0;
+        __syncthreads();
+        const int l = G.hv_plane[pass];
+        for (int i = threadIdx.x; i < (G.ce_ptr[l + 1] - G.ce_ptr[l]) * 18; i += kThreads) {
+          const int ce = G.ce_ptr[l] + i / 18, kk = i % 18, node = G.ce_node[ce];
+          Yh[node * 18 + kk] = ldc(G.Yc + (size_t)ce * 18 + kk);
+          Wh[node * 18 + kk] = ldc(G.Wc + (size_t)ce * 18 + kk);
         }
-        for (int kk = G.pinc_ptr[p]; kk < G.pinc_ptr[p + 1]; kk++) {
-          int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
-          int j = G.pf_j[f];
-          if (j < 0) continue;
-          int o = side ? G.pf_i[f] : j;  // the other pose
-          int oc0 = o / G.SP;
-          for (int q = 0; q < 2; q++) {
-            int bnode = oc0 + q;
-            if (bnode >= G.nc) continue;
-            double hb = hat(o, bnode);
-            if (hb == 0.0) continue;
-            for (int en = lane; en < 36; en += 32) {
-              int r = en / 6, cc = en % 6;
-              // block (p, o) of Hpp: A12 if p is side 0, A12^T otherwise
-              double v = side ? ldc(G.PF + (size_t)f * 120 + 72 + cc * 6 + r) : ldc(G.PF + (size_t)f * 120 + 72 + en);
-              { double* dstp = &A[ac_index(ldm, a * 6 + r, bnode * 6 + cc)]; *dstp = ldc(dstp) + (ha * hb * v); }
+        __syncthreads();
+      }
+      for (long long idx = tid_team(); idx < total; idx += nthr_team()) {
+        const int i = (int)(idx / ldm), j = (int)(idx - (long long)i * ldm);
+        double* out = A + ac_index(ldm, i, j);
+        if (i >= n6 || j >= n6) {   // padding: identity
+          if (pass == 0) *out = (i == j) ? 1.0 : 0.0;
+          continue;
+        }
+        const int a = i / 6, r = i - a * 6, b = j / 6, cc = j - b * 6;
+        double v;
+        if (pass == 0) {
+          v = 0.0;
+          if (a - b <= 1 && b - a <= 1) {   // P^T Hpp_d P on the overlap of the two supports
+            const int plo = max(0, (max(a, b) - 1) * G.SP + 1), phi = min(G.N, (min(a, b) + 1) * G.SP);
+            for (int p = plo; p < phi; p++) {
+              double h = ldc(G.Hpp + (size_t)p * 36 + r * 6 + cc);
+              if (r == cc) h *= (1 + lambda);
+              v += hat(p, a) * hat(p, b) * h;
             }
           }
-        }
-      }
-      __syncwarp();
-      // minus sum over planes touching node a:  Wc[a,l] Hinv_l Wc[b,l]^T
-      for (int t = G.n2ce_ptr[a]; t < G.n2ce_ptr[a + 1]; t++) {
-        int cea = G.n2ce[t];
-        int l = G.ce_plane[cea];
-        double Y[18];  // Wc[a,l] * Hinv  (6x3)
-        {
-          double Wa[18], Hi[9];
-          for (int k = 0; k < 18; k++) Wa[k] = ldc(G.Wc + (size_t)cea * 18 + k);
-          for (int k = 0; k < 9; k++) Hi[k] = ldc(G.Hinv + (size_t)l * 9 + k);
-          for (int r = 0; r < 6; r++)
-            for (int b = 0; b < 3; b++) Y[r * 3 + b] = Wa[r * 3] * Hi[b] + Wa[r * 3 + 1] * Hi[3 + b] + Wa[r * 3 + 2] * Hi[6 + b];
-        }
-        for (int ceb = G.ce_ptr[l]; ceb < G.ce_ptr[l + 1]; ceb++) {
-          int bnode = G.ce_node[ceb];
-          for (int en = lane; en < 36; en += 32) {
-            int r = en / 6, cc = en % 6;
-            const double* wb = G.Wc + (size_t)ceb * 18 + cc * 3;
-            double v = Y[r * 3] * ldc(wb) + Y[r * 3 + 1] * ldc(wb + 1) + Y[r * 3 + 2] * ldc(wb + 2);
-            { double* dstp = &A[ac_index(ldm, a * 6 + r, bnode * 6 + cc)]; *dstp = ldc(dstp) - (v); }
+          const size_t pair = (size_t)a * nc + b;
+          for (int k = G.fp_ptr[pair]; k < G.fp_ptr[pair + 1]; k++) {   // pose-pose blocks of Hpp
+            const int fs = G.fp_f[k], f = fs >> 1, side = fs & 1;
+            const int p = side ? G.pf_j[f] : G.pf_i[f], o = side ? G.pf_i[f] : G.pf_j[f];
+            const double blk = side ? ldc(G.PF + (size_t)f * 120 + 72 + cc * 6 + r) : ldc(G.PF + (size_t)f * 120 + 72 + r * 6 + cc);
+            v += hat(p, a) * hat(o, b) * blk;
           }
+          for (int k = G.lp_ptr[pair]; k < G.lp_ptr[pair + 1]; k++) {   // minus Wc[a,l] Hll^-1 Wc[b,l]^T, light planes
+            const double* y = G.Yc + (size_t)G.lp_cea[k] * 18 + r * 3;
+            const double* w = G.Wc + (size_t)G.lp_ceb[k] * 18 + cc * 3;
+            v -= ldc(y) * ldc(w) + ldc(y + 1) * ldc(w + 1) + ldc(y + 2) * ldc(w + 2);
+          }
+        } else {
+          v = *out;   // written by this same thread in the previous pass
         }
+        if (G.n_hv > 0) {
+          const double* y = Yh + a * 18 + r * 3;
+          const double* w = Wh + b * 18 + cc * 3;
+          v -= y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
+        }
+        *out = v;
       }
     }
     fence_proxy_async();  // A_c is read back by bulk copies in coarse_invert()
@@ -1170,6 +1179,33 @@ struct Phase {
     return nrm;
   }
 
+  // -------- large graphs: vl = Hll_d^-1 * sum(upart) for the heavy planes only (> 8 partial sums), once per PCG
+  // iteration instead of once per pose block inside pose_phase()
+  __device__ void solve_heavy() {
+    const int lane = threadIdx.x & 31;
+    for (int h = warp_team(); h < G.n_heavy; h += nwarp_team()) {
+      const int l = G.heavy[h];
+      if (l < 0) continue;
+      const int t0 = G.upart_ptr[l], n = G.upart_ptr[l + 1] - t0;
+      double uu[3] = {0, 0, 0};
+      for (int tb = t0 + lane; tb < t0 + n; tb += 256) {   // 8 strided partials per lane in flight
+        double pr[8][3];
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) pr[t][b] = (tb + 32 * t < t0 + n) ? ldc(G.upart + (size_t)(tb + 32 * t) * 3 + b) : 0.0;
+#pragma unroll
+        for (int t = 0; t < 8; t++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
+      }
+      for (int b = 0; b < 3; b++) uu[b] = warp_sum(uu[b]);
+      if (lane < 3)
+        G.vl[(size_t)l * 3 + lane] = ldc(G.Hinv + (size_t)l * 9 + lane * 3) * uu[0] + ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 1) * uu[1] +
+                                     ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 2) * uu[2];
+    }
+  }
+
   // number of rounds every CTA of the team runs over its owned pose blocks
   __device__ __forceinline__ int rounds() const { return (G.nblk + c.tsize * kSlots - 1) / (c.tsize * kSlots); }
 
@@ -1256,10 +1292,12 @@ struct Phase {
                 for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
 #pragma unroll
               for (int b = 0; b < 3; b++) vo[b] = Hi[b * 3] * uu[0] + Hi[b * 3 + 1] * uu[1] + Hi[b * 3 + 2] * uu[2];
+            } else if (c.use_tma) {   // large graph: solve_heavy() already reduced this plane
+              for (int b = 0; b < 3; b++) vo[b] = ldc(G.vl + (size_t)l * 3 + b);
             }
           }
         }
-        if (!rhs) {
+        if (!rhs && !c.use_tma) {
           for (int g = wis; g < ng; g += 3) {   // heavy planes: a warp sums the partials
             const int l = G.grp_plane[g0 + g];
             const int t0 = G.upart_ptr[l], n = G.upart_ptr[l + 1] - t0;

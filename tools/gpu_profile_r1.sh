@@ -11,7 +11,7 @@ for cfg in 3 5; do
   ncu --set full --import-source on --clock-control none -k regex:lm_kernel -c 1 -o /tmp/prof_c$cfg python tools/prof1.py $args > gpurun_out/prof_r1_c$cfg.log 2>&1
   ncu -i /tmp/prof_c$cfg.ncu-rep --page raw --csv > gpurun_out/r1_c${cfg}_ncu_raw.csv 2>/dev/null
   ncu -i /tmp/prof_c$cfg.ncu-rep --page details --csv > gpurun_out/r1_c${cfg}_ncu_details.csv 2>/dev/null
-  ncu -i /tmp/prof_c$cfg.ncu-rep --page source --csv --print-source cuda 2>/dev/null | gzip > gpurun_out/r1_c${cfg}_ncu_source.csv.gz
+  ncu -i /tmp/prof_c$cfg.ncu-rep --page source --csv --print-source cuda,sass 2>/dev/null | gzip > gpurun_out/r1_c${cfg}_ncu_source.csv.gz
 done
 python tools/prof1.py 5 2 3 > gpurun_out/c5_timing.log 2>&1
 tail -25 gpurun_out/c5_timing.log
