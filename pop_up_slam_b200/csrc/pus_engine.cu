@@ -451,8 +451,8 @@ static int upload(Solver* s) {
 #define UP(field) if (s->dupload(&d.field, c.field, &bytes) < 0) return -1
     UP(pp_pose); UP(pp_plane); UP(pp_ptr); UP(pp_end); UP(pm2pl); UP(pm_part); UP(ypart_ptr); UP(tile_ptr); UP(blk_part_ptr);
     UP(grp_of_slot); UP(pp_meas); UP(pp_sinf);
-    UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr); UP(heavy);
-    d.n_heavy = (int)c.heavy.size();
+    UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr); UP(heavy); UP(huge);
+    d.n_heavy = c.n_heavy; d.n_huge = c.n_huge;
     UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pf_meas); UP(pf_sinf);
     UP(lp_plane); UP(linc_ptr); UP(linc); UP(lp_meas); UP(lp_sinf);
     UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple);

@@ -155,7 +155,7 @@ struct Compiled {
   int N = 0, M = 0, Epl = 0, Epf = 0, Elp = 0;
   int SP = kCoarseSpacing;
   int nc_pad = 0;  // nc rounded up to whole pivot blocks; the padding nodes carry identity blocks
-  int ntile = 0, nslot = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0, n_hv = 0;
+  int ntile = 0, nslot = 0, nblk = 0, nc = 0, n_upart = 0, n_ypart = 0, nce = 0, ngrp = 0, n_hv = 0, n_heavy = 0, n_huge = 0;
   std::vector<int> pose_node, plane_node;   // idx -> node id
   std::vector<int> node_idx;                // node id -> idx (pose idx or plane idx), -1 dead
   std::vector<double> pose_val, plane_val;  // [N*7], [M*4]
@@ -164,7 +164,7 @@ struct Compiled {
   std::vector<int> pp_fid, pp_pose, pp_plane, pp_ptr, pm2pl, pm_part, ypart_ptr, tile_ptr, blk_part_ptr, grp_of_slot;
   std::vector<double> pp_meas, pp_sinf;
   // plane-major view
-  std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr, pp_end, heavy;
+  std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr, pp_end, heavy, huge;
   int ntile_pl = 0;
   // pose factors (prior / odometry)
   std::vector<int> pf_fid, pf_i, pf_j, pinc_ptr, pinc;
@@ -312,9 +312,15 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     }
     c.n_upart = np;
     for (int l = 0; l < M; l++) { c.pl_ptr[l + 1] += c.pl_ptr[l]; c.upart_ptr[l + 1] += c.upart_ptr[l]; }
-    c.heavy.clear();   // planes with more than 8 partial sums (summed by a warp; once per iteration on large graphs)
-    for (int l = 0; l < M; l++) if (c.upart_ptr[l + 1] - c.upart_ptr[l] > 8) c.heavy.push_back(l);
+    c.heavy.clear(); c.huge.clear();   // planes with more than 8 partial sums are summed by a warp, more than 512 by a CTA
+    for (int l = 0; l < M; l++) {
+      const int n = c.upart_ptr[l + 1] - c.upart_ptr[l];
+      if (n > 512) c.huge.push_back(l);
+      else if (n > 8) c.heavy.push_back(l);
+    }
+    c.n_heavy = (int)c.heavy.size(); c.n_huge = (int)c.huge.size();
     if (c.heavy.empty()) c.heavy.push_back(-1);
+    if (c.huge.empty()) c.huge.push_back(-1);
   }
   // ---- incidence lists ----
   c.pinc_ptr.assign(N + 1, 0);

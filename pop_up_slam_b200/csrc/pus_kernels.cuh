@@ -69,8 +69,8 @@ struct DevGraph {
   // pose-plane edges (pose-major) and plane-major view
   const int *pp_pose, *pp_plane, *pp_ptr, *pp_end, *pm2pl, *pm_part, *ypart_ptr, *tile_ptr, *blk_part_ptr, *grp_of_slot;
   const double *pp_meas, *pp_sinf;
-  const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr, *heavy;
-  int n_heavy;
+  const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr, *heavy, *huge;
+  int n_heavy, n_huge;
   // pose factors / plane priors
   const int *pf_i, *pf_j, *pinc_ptr, *pinc;
   const double *pf_meas, *pf_sinf;
@@ -1182,7 +1182,38 @@ struct Phase {
   // -------- large graphs: vl = Hll_d^-1 * sum(upart) for the heavy planes only (> 8 partial sums), once per PCG
   // iteration instead of once per pose block inside pose_phase()
   __device__ void solve_heavy() {
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    // planes with > 512 partial sums (a ground plane seen from every pose): one CTA each, fixed-order tree
+    for (int hh = c.rank; hh < G.n_huge; hh += c.tsize) {
+      const int l = G.huge[hh];
+      const int t0 = G.upart_ptr[l], n = G.upart_ptr[l + 1] - t0;
+      double* s = reinterpret_cast<double*>(c.smem + kSmRed);
+      double uu[3] = {0, 0, 0};
+      for (int tb = t0 + (int)threadIdx.x; tb < t0 + n; tb += 4 * kThreads) {
+        double pr[4][3];
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) pr[t][b] = (tb + kThreads * t < t0 + n) ? ldc(G.upart + (size_t)(tb + kThreads * t) * 3 + b) : 0.0;
+#pragma unroll
+        for (int t = 0; t < 4; t++)
+#pragma unroll
+          for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
+      }
+      for (int b = 0; b < 3; b++) uu[b] = warp_sum(uu[b]);
+      __syncthreads();
+      if (lane == 0) for (int b = 0; b < 3; b++) s[warp * 4 + b] = uu[b];
+      __syncthreads();
+      if (threadIdx.x < 3) {
+        double tot[3] = {0, 0, 0};
+        for (int w = 0; w < kWarps; w++)
+          for (int b = 0; b < 3; b++) tot[b] += s[w * 4 + b];
+        const int o = threadIdx.x;
+        G.vl[(size_t)l * 3 + o] = ldc(G.Hinv + (size_t)l * 9 + o * 3) * tot[0] + ldc(G.Hinv + (size_t)l * 9 + o * 3 + 1) * tot[1] +
+                                  ldc(G.Hinv + (size_t)l * 9 + o * 3 + 2) * tot[2];
+      }
+      __syncthreads();
+    }
     for (int h = warp_team(); h < G.n_heavy; h += nwarp_team()) {
       const int l = G.heavy[h];
       if (l < 0) continue;
