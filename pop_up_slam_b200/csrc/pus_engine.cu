@@ -85,7 +85,12 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
     while (it < G.prm.pcg_max_iter) {
       ft.sync();
       ph.update_direction(cur, beta);
-      ph.sweep_planes(G.z, G.pv[cur], beta, G.zc);
+      if (c.use_tma) {   // large graphs: publish the new direction first, the sweep then gathers 6 values per edge
+        team_barrier(c);
+        ph.sweep_planes(G.pv[cur ^ 1], nullptr, 0.0);
+      } else {
+        ph.sweep_planes(G.z, G.pv[cur], beta, G.zc);
+      }
       team_barrier(c);
       if (c.use_tma) { ph.solve_heavy(); team_barrier(c); }
       ft.lap(16);

@@ -824,6 +824,7 @@ struct Phase {
       double* out = G.Binv + (size_t)k * kBlockDim * kBlockDim;
       for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) out[i] = inv[(i / kBlockDim) * LD + i % kBlockDim];
     }
+    fence_proxy_async();  // Binv is streamed by bulk copies in precondition() on large graphs
     __syncthreads();
   }
 
@@ -1096,28 +1097,67 @@ struct Phase {
   // (zc != nullptr: the gathered vector also gets its coarse part P*zc added on the fly, see precondition())
   __device__ void sweep_planes(const double* va, const double* vb, double beta, const double* zc = nullptr) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    // large graphs: the warp's next Wt tile (4608 contiguous bytes) is fetched by one bulk async copy into the
-    // other staging buffer while the current one is consumed
-    double* buf = reinterpret_cast<double*>(c.smem + kSmTma) + warp * 2 * kWStride;
-    unsigned long long* bar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + warp * 2;
     const int step = nwarp_team();
-    int st = 0;
     if (c.use_tma) {
+      // Large graphs: a warp owns several tiles.  Software pipeline, three tiles deep: the Wt tile after this one
+      // (4608 contiguous bytes) is in flight as one bulk async copy into the other staging buffer, the per-edge
+      // gathers of the next tile are issued before this tile is multiplied, and the edge indices are read two tiles
+      // ahead -- no dependent-load latency is exposed in steady state.
+      double* buf = reinterpret_cast<double*>(c.smem + kSmTma) + warp * 2 * kWStride;
+      unsigned long long* bar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + warp * 2;
+      int tile = warp_team(), st = 0;
       __syncwarp();
-      if (lane == 0 && warp_team() < G.ntile_pl) {
+      if (lane == 0 && tile < G.ntile_pl) {
         fence_proxy_async();
-        tma_load_1d(buf, G.Wt + (size_t)warp_team() * kWStride, kTileBytes, bar);
+        tma_load_1d(buf, G.Wt + (size_t)tile * kWStride, kTileBytes, bar);
       }
+      // (on large graphs the callers pass one fully formed vector: vb == nullptr, zc == nullptr)
+      int keyC = -1, pC = 0, keyN = -1, pN = 0;
+      if (tile < G.ntile_pl) { keyC = G.pl_plane[tile * 32 + lane]; pC = G.pl_pose[tile * 32 + lane]; }
+      if (tile + step < G.ntile_pl) { keyN = G.pl_plane[(tile + step) * 32 + lane]; pN = G.pl_pose[(tile + step) * 32 + lane]; }
+      double x[6] = {0, 0, 0, 0, 0, 0};
+      if (keyC >= 0)
+        for (int a = 0; a < 6; a++) x[a] = ldc(va + (size_t)pC * 6 + a);
+      for (; tile < G.ntile_pl; tile += step, st ^= 1) {
+        if (lane == 0 && tile + step < G.ntile_pl)
+          tma_load_1d(buf + (st ^ 1) * kWStride, G.Wt + (size_t)(tile + step) * kWStride, kTileBytes, bar + (st ^ 1));
+        int keyNN = -1, pNN = 0;
+        if (tile + 2 * step < G.ntile_pl) { keyNN = G.pl_plane[(tile + 2 * step) * 32 + lane]; pNN = G.pl_pose[(tile + 2 * step) * 32 + lane]; }
+        double xn[6] = {0, 0, 0, 0, 0, 0};   // gathers of the next tile, consumed in the next iteration
+        if (keyN >= 0) {
+#pragma unroll
+          for (int a = 0; a < 6; a++) xn[a] = ldc(va + (size_t)pN * 6 + a);
+        }
+        double u[3] = {0, 0, 0};
+        mbar_wait(bar + st, (c.tma_par >> st) & 1u);
+        c.tma_par ^= (1u << st);
+        if (keyC >= 0) {
+          const double* wt = buf + st * kWStride + lane;
+#pragma unroll
+          for (int a = 0; a < 6; a++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) u[b] += wt[(a * 3 + b) * 32] * x[a];
+        }
+        seg_suffix_sum<3>(keyC, u);
+        const int pk = __shfl_up_sync(0xffffffffu, keyC, 1);
+        if (keyC >= 0 && (lane == 0 || pk != keyC)) {
+          double* o = G.upart + (size_t)G.pl_part[tile * 32 + lane] * 3;
+          o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+        }
+#pragma unroll
+        for (int a = 0; a < 6; a++) x[a] = xn[a];
+        keyC = keyN; pC = pN; keyN = keyNN; pN = pNN;
+        __syncwarp();  // every lane is done with this stage before lane 0 refills it
+      }
+      return;
     }
-    for (int tile = warp_team(); tile < G.ntile_pl; tile += step, st ^= 1) {
-      if (c.use_tma && lane == 0 && tile + step < G.ntile_pl)
-        tma_load_1d(buf + (st ^ 1) * kWStride, G.Wt + (size_t)(tile + step) * kWStride, kTileBytes, bar + (st ^ 1));
+    for (int tile = warp_team(); tile < G.ntile_pl; tile += step) {
       int s = tile * 32 + lane;
       int key = G.pl_plane[s];
       double u[3] = {0, 0, 0};
-      double x[6] = {0, 0, 0, 0, 0, 0};
       if (key >= 0) {
         int p = G.pl_pose[s];
+        double x[6];
         for (int a = 0; a < 6; a++) x[a] = ldc(va + (size_t)p * 6 + a);
         if (vb) for (int a = 0; a < 6; a++) x[a] += beta * ldc(vb + (size_t)p * 6 + a);
         if (zc) {
@@ -1127,18 +1167,6 @@ struct Phase {
           const double* z1 = zc + (size_t)min(c0 + 1, G.nc - 1) * 6;
           for (int a = 0; a < 6; a++) x[a] += h0 * ldc(z0 + a) + h1 * ldc(z1 + a);
         }
-      }
-      if (c.use_tma) {
-        mbar_wait(bar + st, (c.tma_par >> st) & 1u);
-        c.tma_par ^= (1u << st);
-        if (key >= 0) {
-          const double* wt = buf + st * kWStride + lane;
-#pragma unroll
-          for (int a = 0; a < 6; a++)
-#pragma unroll
-            for (int b = 0; b < 3; b++) u[b] += wt[(a * 3 + b) * 32] * x[a];
-        }
-      } else if (key >= 0) {
         const double* wt = G.Wt + (size_t)tile * kWStride + lane;
 #pragma unroll
         for (int a = 0; a < 6; a++)
@@ -1151,7 +1179,6 @@ struct Phase {
         double* o = G.upart + (size_t)G.pl_part[s] * 3;
         o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
       }
-      __syncwarp();  // every lane is done with this stage before lane 0 refills it
     }
   }
 
@@ -1289,12 +1316,18 @@ struct Phase {
       const bool on = live && (p < G.N);
       __syncthreads();
       if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
-      if (live && c.use_tma && lane == 0) {
-        // first W tile of this warp: in flight while the plane-group vectors are formed
+      // first W tile of this warp (large graphs: bulk copy) and its edge indices: in flight while the plane-group
+      // vectors are formed
+      int keyN = -1, gosN = 0, partN = 0;
+      if (live) {
         const int t0 = G.tile_ptr[k], nt = G.tile_ptr[k + 1] - t0;
         if (wis < nt) {
-          fence_proxy_async();
-          tma_load_1d(tbuf, G.W + (size_t)(t0 + wis) * kWStride, kTileBytes, tbar);
+          if (c.use_tma && lane == 0) {
+            fence_proxy_async();
+            tma_load_1d(tbuf, G.W + (size_t)(t0 + wis) * kWStride, kTileBytes, tbar);
+          }
+          const int e = (t0 + wis) * 32 + lane;
+          keyN = G.pp_pose[e]; gosN = G.grp_of_slot[e]; partN = G.pm_part[e];
         }
       }
       if (live) {
@@ -1358,15 +1391,19 @@ struct Phase {
       if (live) {
         const int t0 = G.tile_ptr[k], nt = G.tile_ptr[k + 1] - t0, part0 = G.blk_part_ptr[k];
         int st = 0;
+        // (edge indices are read one tile ahead: static arrays whose latency would otherwise be exposed per tile)
         for (int t = wis; t < nt; t += 3, st ^= 1) {
           if (c.use_tma && lane == 0 && t + 3 < nt)
             tma_load_1d(tbuf + (st ^ 1) * kWStride, G.W + (size_t)(t0 + t + 3) * kWStride, kTileBytes, tbar + (st ^ 1));
-          const int e = (t0 + t) * 32 + lane;
-          const int key = G.pp_pose[e];
+          const int key = keyN, gos = gosN, part = partN;
+          if (t + 3 < nt) {
+            const int e = (t0 + t + 3) * 32 + lane;
+            keyN = G.pp_pose[e]; gosN = G.grp_of_slot[e]; partN = G.pm_part[e];
+          }
           double y[6] = {0, 0, 0, 0, 0, 0};
           double v0 = 0, v1 = 0, v2 = 0;
           if (key >= 0) {
-            const double* v = vg + (slot * kMaxGrp + G.grp_of_slot[e]) * 3;
+            const double* v = vg + (slot * kMaxGrp + gos) * 3;
             v0 = v[0]; v1 = v[1]; v2 = v[2];
           }
           if (c.use_tma) {
@@ -1385,7 +1422,7 @@ struct Phase {
           seg_suffix_sum<6>(key, y);
           int pk = __shfl_up_sync(0xffffffffu, key, 1);
           if (key >= 0 && (lane == 0 || pk != key)) {
-            double* o = yp + (slot * kMaxPart + (G.pm_part[e] - part0)) * 6;
+            double* o = yp + (slot * kMaxPart + (part - part0)) * 6;
             for (int a = 0; a < 6; a++) o[a] = y[a];
           }
           __syncwarp();  // stage consumed by every lane before it is refilled
@@ -1581,7 +1618,76 @@ struct Phase {
       }
     }
     lap(14);
-    for (int rd = 0; rd < rounds(); rd++) {
+    const int nrd = rounds();
+    const int sr_off = kSmRc + ((ldm * 8 + 127) / 128) * 128;   // staged residuals of all rounds, after the coarse residual
+    if (c.use_tma && sr_off + nrd * kSlots * kBlockDim * 8 <= kSmTma) {
+      // Large graphs: (A) update x, r of every owned pose and keep the new residuals of all rounds in shared memory
+      // (loads of three rounds in flight together), then (B) stream the owned dense blocks Binv[k] through the
+      // two 72 KB staging buffers with one bulk async copy each (the next block in flight while this one is applied).
+      double* sR = reinterpret_cast<double*>(c.smem + sr_off);
+      __syncthreads();
+      for (int rd0 = 0; rd0 < nrd; rd0 += 3) {
+        double vr[3], vp[3], vq[3], vx[3];
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const int rd = rd0 + t, k = c.rank + c.tsize * (slot + kSlots * rd), p = k * kBlockPoses + u / 6;
+          const bool on = (rd < nrd) && (slot < kSlots) && (k < G.nblk) && (p < G.N);
+          const size_t o = (size_t)p * 6 + u % 6;
+          vr[t] = on ? ldc(G.r + o) : 0.0;
+          vp[t] = (on && !first) ? ldc(pvec + o) : 0.0;
+          vq[t] = (on && !first) ? ldc(G.q + o) : 0.0;
+          vx[t] = (on && !first) ? ldc(G.x + o) : 0.0;
+        }
+#pragma unroll
+        for (int t = 0; t < 3; t++) {
+          const int rd = rd0 + t, k = c.rank + c.tsize * (slot + kSlots * rd), p = k * kBlockPoses + u / 6;
+          if (rd >= nrd || slot >= kSlots) continue;
+          const bool on = (k < G.nblk) && (p < G.N);
+          double rn = vr[t];
+          if (on && !first) {
+            const size_t o = (size_t)p * 6 + u % 6;
+            rn -= alpha * vq[t];
+            G.x[o] = vx[t] + alpha * vp[t];
+            G.r[o] = rn;
+          }
+          sR[(rd * kSlots + slot) * kBlockDim + u] = on ? rn : 0.0;
+        }
+      }
+      __syncthreads();
+      unsigned long long* gbar = reinterpret_cast<unsigned long long*>(c.smem + kSmGjBar);
+      double* bbuf = reinterpret_cast<double*>(c.smem + kSmTma);
+      constexpr unsigned kBlockBytes = kBlockDim * kBlockDim * 8;
+      static_assert(2 * kBlockBytes <= kSmTmaEnd - kSmTma, "two dense blocks must fit the staging area");
+      const int nown = (G.nblk - c.rank + c.tsize - 1) / c.tsize;   // owned blocks: k = rank + tsize * ib
+      if (tid == 0 && nown > 0) tma_load_1d(bbuf, G.Binv + (size_t)c.rank * kBlockDim * kBlockDim, kBlockBytes, gbar);
+      for (int ib = 0; ib < nown; ib++) {
+        const int k = c.rank + c.tsize * ib;
+        if (tid == 0 && ib + 1 < nown)
+          tma_load_1d(bbuf + ((ib + 1) & 1) * kBlockDim * kBlockDim, G.Binv + (size_t)(k + c.tsize) * kBlockDim * kBlockDim, kBlockBytes,
+                      gbar + ((ib + 1) & 1));
+        const double* rv = sR + (size_t)ib * kBlockDim;   // (ib = slot + kSlots * rd: the staging order of part A)
+        const int np = min(kBlockPoses, G.N - k * kBlockPoses);
+        mbar_wait(gbar + (ib & 1), (c.gj_par >> (ib & 1)) & 1u);
+        c.gj_par ^= (1u << (ib & 1));
+        if (tid < kBlockDim) {
+          const double* B = bbuf + (ib & 1) * kBlockDim * kBlockDim + tid;
+          double zl = 0;
+#pragma unroll 8
+          for (int j = 0; j < kBlockDim; j++) zl += B[j * kBlockDim] * rv[j];
+          const int p = k * kBlockPoses + tid / 6;
+          if (p < G.N) {
+            G.z[(size_t)p * 6 + tid % 6] = zl;
+            dot += rv[tid] * zl;
+          }
+        } else if (tid >= 128 && tid < 128 + 12) {
+          restrict_block(rv, 0, tid - 128, k, np, rc_new);
+        }
+        __syncthreads();   // the buffer may be refilled
+      }
+      lap(15);
+      return dot;
+    }
+    for (int rd = 0; rd < nrd; rd++) {
       int k = c.rank + c.tsize * (slot + kSlots * rd);
       int p = k * kBlockPoses + u / 6, row = u % 6;
       bool live = (slot < kSlots) && (k < G.nblk);
