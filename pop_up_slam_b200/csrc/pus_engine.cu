@@ -458,9 +458,9 @@ static int upload(Solver* s) {
     UP(grp_of_slot); UP(pp_meas); UP(pp_sinf);
     UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr); UP(heavy); UP(huge);
     d.n_heavy = c.n_heavy; d.n_huge = c.n_huge;
-    UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pf_meas); UP(pf_sinf);
+    UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pnbr); UP(pf_meas); UP(pf_sinf);
     UP(lp_plane); UP(linc_ptr); UP(linc); UP(lp_meas); UP(lp_sinf);
-    UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple);
+    UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple); UP(grp_info);
     UP(ce_ptr); UP(ce_node); UP(ce_plane); UP(ce_lo); UP(ce_hi); UP(n2ce_ptr); UP(n2ce);
     UP(hv_plane); UP(lp_ptr); UP(lp_cea); UP(lp_ceb); UP(fp_ptr); UP(fp_f);
     d.n_hv = c.n_hv;

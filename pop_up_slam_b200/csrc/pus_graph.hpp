@@ -167,13 +167,13 @@ struct Compiled {
   std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr, pp_end, heavy, huge;
   int ntile_pl = 0;
   // pose factors (prior / odometry)
-  std::vector<int> pf_fid, pf_i, pf_j, pinc_ptr, pinc;
+  std::vector<int> pf_fid, pf_i, pf_j, pinc_ptr, pinc, pnbr;
   std::vector<double> pf_meas, pf_sinf;
   // plane priors
   std::vector<int> lp_fid, lp_plane, linc_ptr, linc;
   std::vector<double> lp_meas, lp_sinf;
   // dense-block groups: per pose block, its edges grouped by plane
-  std::vector<int> blk_grp_ptr, grp_plane, grp_mem_ptr, grp_mem, blk_simple;
+  std::vector<int> blk_grp_ptr, grp_plane, grp_mem_ptr, grp_mem, blk_simple, grp_info;
   // coarse (hat) space: (plane, coarse node) pairs
   std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
   std::vector<int> hv_plane, lp_ptr, lp_cea, lp_ceb, fp_ptr, fp_f;   // coarse assembly: heavy planes, per node-pair lists
@@ -334,6 +334,22 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
       if (c.pf_j[f] >= 0) c.pinc[fill[c.pf_j[f]]++] = (f << 1) | 1;
     }
   }
+  // per pose: its first two pose-pose neighbours resolved (factor*2+side, other pose) and where the generic
+  // incidence loop resumes -- one 32-byte record instead of a four-level index chain in the PCG pose phase
+  c.pnbr.assign((size_t)N * 8, -1);
+  for (int p = 0; p < N; p++) {
+    int nf = 0, kk = c.pinc_ptr[p];
+    const int i1 = c.pinc_ptr[p + 1];
+    for (; kk < i1 && nf < 2; kk++) {
+      const int inc = c.pinc[kk], f = inc >> 1, side = inc & 1;
+      if (c.pf_j[f] < 0) continue;
+      c.pnbr[(size_t)p * 8 + 2 * nf] = inc;
+      c.pnbr[(size_t)p * 8 + 2 * nf + 1] = side ? c.pf_i[f] : c.pf_j[f];
+      nf++;
+    }
+    c.pnbr[(size_t)p * 8 + 4] = kk;
+    c.pnbr[(size_t)p * 8 + 5] = i1;
+  }
   c.linc_ptr.assign(M + 1, 0);
   for (int f = 0; f < c.Elp; f++) c.linc_ptr[c.lp_plane[f] + 1]++;
   for (int l = 0; l < M; l++) c.linc_ptr[l + 1] += c.linc_ptr[l];
@@ -376,6 +392,13 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   }
   c.grp_mem_ptr.push_back((int)c.grp_mem.size());
   c.ngrp = (int)c.grp_plane.size();
+  c.grp_info.assign((size_t)std::max(1, c.ngrp) * 4, 0);   // {plane, first partial sum, number of partial sums, -}
+  for (int g = 0; g < c.ngrp; g++) {
+    const int l = c.grp_plane[g];
+    c.grp_info[(size_t)g * 4] = l;
+    c.grp_info[(size_t)g * 4 + 1] = c.upart_ptr[l];
+    c.grp_info[(size_t)g * 4 + 2] = c.upart_ptr[l + 1] - c.upart_ptr[l];
+  }
   // ---- coarse (plane, node) pairs ----
   c.SP = coarse_spacing(N);
   const int SPc = c.SP;

@@ -72,12 +72,12 @@ struct DevGraph {
   const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr, *heavy, *huge;
   int n_heavy, n_huge;
   // pose factors / plane priors
-  const int *pf_i, *pf_j, *pinc_ptr, *pinc;
+  const int *pf_i, *pf_j, *pinc_ptr, *pinc, *pnbr;
   const double *pf_meas, *pf_sinf;
   const int *lp_plane, *linc_ptr, *linc;
   const double *lp_meas, *lp_sinf;
   // dense-block groups, coarse pairs
-  const int *blk_grp_ptr, *grp_plane, *grp_mem_ptr, *grp_mem, *blk_simple;
+  const int *blk_grp_ptr, *grp_plane, *grp_mem_ptr, *grp_mem, *blk_simple, *grp_info;
   const int *ce_ptr, *ce_node, *ce_plane, *ce_lo, *ce_hi, *n2ce_ptr, *n2ce;
   const int *hv_plane, *lp_ptr, *lp_cea, *lp_ceb, *fp_ptr, *fp_f;
   int n_hv;
@@ -1308,13 +1308,29 @@ struct Phase {
     double* tbuf = reinterpret_cast<double*>(c.smem + kSmTma) + (tid >> 5) * 2 * kWStride;  // TMA staging (large graphs)
     unsigned long long* tbar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + (tid >> 5) * 2;
     double dot = 0;
+    // plane-group record of this thread for the coming round (static data, read one round ahead)
+    int g0N = 0, ngN = 0;
+    int4 giN = make_int4(0, 0, 0, 0);
+    auto next_groups = [&](int rd) {
+      const int k = c.rank + c.tsize * (slot + kSlots * rd);
+      g0N = 0; ngN = 0;
+      if (rd < rounds() && slot < kSlots && k < G.nblk) {
+        g0N = G.blk_grp_ptr[k];
+        ngN = G.blk_grp_ptr[k + 1] - g0N;
+        if (u < ngN) giN = *reinterpret_cast<const int4*>(G.grp_info + (size_t)(g0N + u) * 4);
+      }
+    };
+    next_groups(0);
     for (int rd = 0; rd < rounds(); rd++) {
       const int k = c.rank + c.tsize * (slot + kSlots * rd);
       const bool live = (slot < kSlots) && (k < G.nblk);
       const int p = k * kBlockPoses + u / 6, row = u % 6;
       const int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
       const bool on = live && (p < G.N);
+      const int g0 = g0N, ng = ngN;
+      const int4 gi0 = giN;
       __syncthreads();
+      next_groups(rd + 1);
       if (slot < kSlots) sA[slot * kBlockDim + u] = 0.0;
       // first W tile of this warp (large graphs: bulk copy) and its edge indices: in flight while the plane-group
       // vectors are formed
@@ -1333,14 +1349,14 @@ struct Phase {
       if (live) {
         // plane-group vectors: one thread per group when the plane has <= 8 partial sums (all loads in one
         // batch), one warp per group for heavy planes (the ground plane is seen from every pose)
-        const int g0 = G.blk_grp_ptr[k], ng = G.blk_grp_ptr[k + 1] - g0;
         for (int g = u; g < ng; g += kBlockDim) {
-          const int l = G.grp_plane[g0 + g];
+          const int4 gi = (g == u) ? gi0 : *reinterpret_cast<const int4*>(G.grp_info + (size_t)(g0 + g) * 4);
+          const int l = gi.x;
           double* vo = vg + (slot * kMaxGrp + g) * 3;
           if (rhs) {
             for (int b = 0; b < 3; b++) vo[b] = ldc(G.vl + (size_t)l * 3 + b);
           } else {
-            const int t0 = G.upart_ptr[l], n = G.upart_ptr[l + 1] - t0;
+            const int t0 = gi.y, n = gi.z;
             if (n <= 8) {
               double pr[8][3], Hi[9];
 #pragma unroll
@@ -1450,21 +1466,16 @@ struct Phase {
             v += h * pc;
           }
           {
-            // pose-pose blocks: the first two neighbours (the odometry chain) are loaded together, the rest loop
-            const int i0 = G.pinc_ptr[p], i1 = G.pinc_ptr[p + 1];
-            int nf = 0, kk = i0;
-            const double* Ab[2] = {nullptr, nullptr};
-            const double* xo[2] = {nullptr, nullptr};
-            int sd[2] = {0, 0};
-            for (; kk < i1 && nf < 2; kk++) {
-              int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
-              int j = G.pf_j[f];
-              if (j < 0) continue;
-              Ab[nf] = G.PF + (size_t)f * 120 + 72;
-              xo[nf] = pvec + (size_t)(side ? G.pf_i[f] : j) * 6;
-              sd[nf] = side;
-              nf++;
-            }
+            // pose-pose blocks: the first two neighbours (the odometry chain) come resolved from the host-built
+            // record and are loaded together, the rest loop over the incidence list
+            const int4 nb = *reinterpret_cast<const int4*>(G.pnbr + (size_t)p * 8);
+            const int2 nr = *reinterpret_cast<const int2*>(G.pnbr + (size_t)p * 8 + 4);
+            const int i1 = nr.y;
+            int kk = nr.x;
+            const int nf = (nb.x >= 0) + (nb.z >= 0);
+            const double* Ab[2] = {G.PF + (size_t)(max(nb.x, 0) >> 1) * 120 + 72, G.PF + (size_t)(max(nb.z, 0) >> 1) * 120 + 72};
+            const double* xo[2] = {pvec + (size_t)max(nb.y, 0) * 6, pvec + (size_t)max(nb.w, 0) * 6};
+            const int sd[2] = {nb.x & 1, nb.z & 1};
             double av[2][6], xv[2][6];
 #pragma unroll
             for (int n2 = 0; n2 < 2; n2++)
