@@ -31,7 +31,27 @@ import numpy as np  # noqa: E402
 from pop_up_slam_b200 import graphgen as gg  # noqa: E402
 
 WORKLOAD = "config3_corridor_5000p_500pl_50000e_huber"
-NCU_DRAM_BYTES_PER_LAUNCH = 702.7e6   # profiles/README.md: the solve is L2-resident, DRAM traffic << algorithmic bytes
+
+
+def ncu_dram_bytes():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one lm_kernel launch on this workload, from the committed
+    `ncu --set full` capture (profiles/r1_c3_ncu_raw.csv); None if the file is missing."""
+    import csv
+    path = os.path.join(ROOT, "profiles", "r1_c3_ncu_raw.csv")
+    try:
+        rows = list(csv.reader(open(path)))
+        hdr, units, vals = rows[0], rows[1], rows[2]
+        scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "Tbyte": 1e12}
+        tot = 0.0
+        for name in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            i = hdr.index(name)
+            tot += float(vals[i]) * scale[units[i]]
+        return tot
+    except Exception:
+        return None
+
+
+NCU_DRAM_BYTES_PER_LAUNCH = ncu_dram_bytes()   # the solve is L2-resident: DRAM traffic << algorithmic bytes
 
 
 def roofline_bytes(dims, relin, chi2_evals, pcg_iters):
@@ -168,6 +188,7 @@ def main():
     ap.add_argument("--impl", default="native", choices=["native", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-batch64", action="store_true")
+    ap.add_argument("--no-stress", action="store_true", help="skip the config-5 (HBM-bound) leg")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -303,9 +324,47 @@ def main():
             line["batch64"] = bench_batch64(capi, GpuGraphAPI, local_rank, stream, world, rank)
         except Exception as e:  # report, never hide
             line["batch64"] = {"error": str(e)}
+    if not args.no_stress and world == 1:
+        try:
+            line["stress_c5"] = bench_stress(GpuGraphAPI, local_rank, stream)
+        except Exception as e:  # report, never hide
+            line["stress_c5"] = {"error": str(e)}
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_stress(GpuGraphAPI, device, stream):
+    """BASELINE config 5 (50 k poses / 5 k planes / 1 M edges): the HBM-bound graph.  Three LM iterations, resident,
+    CUDA events; algorithmic bytes as for the headline roofline plus the 96x96 preconditioner blocks the PCG streams."""
+    import torch
+    g = gg.make_config(5, seed=0, max_iterations=3)
+    a = GpuGraphAPI(device=device)
+    a.set_stream(stream.cuda_stream)
+    gg.build_bulk(a, g)
+    gg.configure(a, g)
+    a.upload()
+    a.solve_resident()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    reps = 2
+    e0.record(stream)
+    for _ in range(reps):
+        it = a.solve_resident()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    st = a.stats()
+    dims = g.dims()
+    nbytes, per = roofline_bytes(dims, st["relinearizations"], st["chi2_evals"], st["pcg_iterations"])
+    binv = st["pcg_iterations"] * ((dims["N"] + 15) // 16) * 96 * 96 * 8
+    peak, peak_src = measured_peak_gbs()
+    return {"workload": "BASELINE config 5: 50k poses / 5k planes / 1M pose-plane + 50k odometry edges, 3 LM iterations",
+            "ms_per_solve": ms, "lm_iterations": int(it), "pcg_iterations": st["pcg_iterations"],
+            "ms_per_pcg_iteration": ms / max(1, st["pcg_iterations"]),
+            "algorithmic_gbs": nbytes / (ms * 1e-3) / 1e9, "frac": nbytes / (ms * 1e-3) / 1e9 / peak,
+            "with_preconditioner_blocks_gbs": (nbytes + binv) / (ms * 1e-3) / 1e9,
+            "with_preconditioner_blocks_frac": (nbytes + binv) / (ms * 1e-3) / 1e9 / peak,
+            "peak": peak, "peak_source": peak_src, "bytes_per_unit": per, "grid_ctas": st["grid_ctas"]}
 
 
 def bench_batch64(capi, GpuGraphAPI, device, stream, world, rank):
