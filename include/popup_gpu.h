@@ -57,7 +57,12 @@ typedef struct pus_solver_options {
   int pcg_max_iter;    /* default 2000 */
   int ctas_per_sm;     /* persistent grid = ctas_per_sm * #SM, 0 = auto */
   int team_ctas;       /* CTAs cooperating on one graph; 0 = auto (whole grid for one graph) */
-  int reserved[4];
+  int reserved[4];     /* diagnostics, all 0 by default:
+                        *   [0] = 1  rebuild the preconditioner for every linear solve (no lazy refresh)
+                        *   [1] = 1  no PCG warm start after a rejected LM step
+                        *   [2]      bit 0: sub-phase timers in pus_stats.phase_ms[13..23]; bit 1: always stage W / Wt
+                        *            tiles by bulk async copy (the large-graph data path); bit 2: never
+                        *   [3] > 0  lazy-refresh threshold in percent of the post-build iteration count (default 200) */
 } pus_solver_options;
 
 typedef struct pus_stats {

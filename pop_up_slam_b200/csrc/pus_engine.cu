@@ -374,8 +374,6 @@ struct Solver {
     prop.lm_lambda0 = 1e-6; prop.lm_lambda_factor = 10.; prop.mod_update = 1; prop.mod_batch = 100; prop.mod_solve = 1;
     std::memset(&opt, 0, sizeof(opt));
     opt.pcg_rel_tol = 1e-8; opt.pcg_max_iter = 2000;   // 4 decades under the 1e-4 parity bar
-    if (const char* e = std::getenv("PUS_PCG_REL_TOL")) opt.pcg_rel_tol = std::atof(e);  // experiment hooks
-    if (const char* e = std::getenv("PUS_REFRESH_PCT")) opt.reserved[3] = std::atoi(e);
     std::memset(&stats, 0, sizeof(stats));
     std::memset(&res, 0, sizeof(res));
     std::memset(&hd, 0, sizeof(hd));

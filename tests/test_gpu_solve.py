@@ -117,6 +117,41 @@ def test_repeated_observations_of_one_plane():
     compare(gpu, orc, ids[0], ids[1])
 
 
+def test_config3_full_size_first_iterations():
+    """BASELINE config 3 at full size (5 000 poses / 500 planes / 50 000 + 5 000 edges, Huber): the first six LM trial
+    steps follow the oracle (analytic Jacobians; beyond ~10 iterations the reference's own accept / reject sequence on
+    this non-convergent problem is chaotic in the last bits)."""
+    g = gg.make_config(3, seed=0, max_iterations=6)
+    gpu, orc = GpuGraphAPI(), OracleAPI()
+    orc.set_jacobian_mode(1)
+    ig, io = gg.build_bulk(gpu, g), gg.build_bulk(orc, g)
+    gg.configure(gpu, g)
+    gg.configure(orc, g)
+    assert gpu.batch_optimize() == orc.batch_optimize()
+    tg, to = gpu.trace(), orc.trace()
+    assert np.array_equal(tg["accepted"], to["accepted"])
+    assert np.allclose(tg["chi2_new"], to["chi2_new"], rtol=1e-6)
+    compare(gpu, orc, ig, io)
+
+
+def test_large_graph_streaming_path():
+    """a graph big enough for the large-graph data path chosen automatically (12 000 poses / 1 200 planes / 240 000
+    edges: several plane-major tiles per warp and two rounds of pose blocks per CTA, so the bulk-async-copy staging of
+    W / Wt / the dense preconditioner blocks, the heavy-plane reduction and the staged residuals all run)."""
+    g = gg.make_config(5, seed=0, n_poses=12000, n_planes=1200, max_iterations=3)
+    gpu, orc = GpuGraphAPI(), OracleAPI()
+    orc.set_jacobian_mode(1)
+    ig, io = gg.build_bulk(gpu, g), gg.build_bulk(orc, g)
+    gg.configure(gpu, g)
+    gg.configure(orc, g)
+    assert gpu.batch_optimize() == orc.batch_optimize()
+    tg, to = gpu.trace(), orc.trace()
+    assert np.array_equal(tg["accepted"], to["accepted"])
+    assert np.allclose(tg["chi2_new"], to["chi2_new"], rtol=1e-6)
+    compare(gpu, orc, ig, io)
+    assert gpu.stats()["grid_ctas"] >= 120
+
+
 def test_gauss_newton_and_update_match_oracle():
     g = gg.make_config(2, seed=1)
     for which in ("gn", "update"):

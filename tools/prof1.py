@@ -11,6 +11,8 @@ g = gg.make_config(cfg, seed=0, **kw)
 a = GpuGraphAPI(); gg.build_bulk(a, g); gg.configure(a, g)
 import ctypes
 o = a.get_solver_options(); o.reserved[2] = int(sys.argv[4]) if len(sys.argv)>4 else 0
+if len(sys.argv)>5: o.pcg_rel_tol = float(sys.argv[5])
+if len(sys.argv)>6: o.reserved[3] = int(sys.argv[6])
 a._chk(a.lib.pus_set_solver_options(a.h, ctypes.byref(o)))
 a.upload()
 for _ in range(reps):
