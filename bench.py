@@ -319,6 +319,10 @@ def main():
         line["cpu_baseline"] = cb
         line["solve"]["chi2_final_cpu_numeric_jacobians"] = cb["chi2_final"]
         line["speedup_vs_cpu"] = {"resident": value / cb["value"], "e2e": e2e_value / cb["value"]}
+        try:
+            line["measurement_refresh"] = bench_refresh(api, orc, g, ids)
+        except Exception as e:  # report, never hide
+            line["measurement_refresh"] = {"error": str(e)}
     if not args.no_batch64:
         try:
             line["batch64"] = bench_batch64(capi, GpuGraphAPI, local_rank, stream, world, rank)
@@ -332,6 +336,31 @@ def main():
     print(json.dumps(line))
     if world > 1:
         dist.destroy_process_group()
+
+
+def bench_refresh(api, orc, g, ids):
+    """SURVEY 8f.1: Mapper_mono::update_plane_measurement over every frame of the bench graph (10 ground segments per
+    frame, every pose-plane factor re-measured), host segments in -> new measurements out, GPU entry point vs the
+    oracle's restatement on one host core."""
+    rng = np.random.default_rng(0)
+    nf = g.n_poses
+    nseg = np.full(nf, 10)
+    seg_ptr = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int32)
+    n = int(seg_ptr[-1])
+    segs = np.stack([rng.uniform(0, 640, n), rng.uniform(300, 480, n), rng.uniform(0, 640, n), rng.uniform(300, 480, n)], axis=1).astype(np.float32)
+    invK = np.linalg.inv(np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]])).astype(np.float32)
+    mf = g.pp_pose.astype(np.int32)
+    mr = (np.arange(len(mf)) % 11).astype(np.int32)
+    t_gpu = []
+    for _ in range(5):
+        t0 = time.perf_counter()
+        api.refresh_plane_measurements(ids["pose_ids"], seg_ptr, segs, invK, ids["pp_fids"], mf, mr)
+        t_gpu.append(time.perf_counter() - t0)
+    t0 = time.perf_counter()
+    orc.refresh_plane_measurements(ids["pose_ids"], seg_ptr, segs, invK, ids["pp_fids"], mf, mr)
+    t_cpu = time.perf_counter() - t0
+    return {"frames": int(nf), "segments": n, "factors_refreshed": int(len(mf)), "gpu_ms": 1e3 * statistics.median(t_gpu),
+            "cpu_port_ms": 1e3 * t_cpu, "timed": "wall clock around the C-ABI call incl. H2D of the segments and D2H of the new measurements"}
 
 
 def bench_stress(GpuGraphAPI, device, stream):

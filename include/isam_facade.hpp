@@ -384,6 +384,7 @@ class Pose3d_Plane3d_Factor : public FactorT<Plane3d> {   // isam_plane3d.h:221-
     if (relative) throw std::runtime_error("Pose3d_Plane3d_Factor: relative parameterisation is not supported (pop_planar_slam builds with useRelative = false, Mapping.cpp:21)");
     _nodes.push_back(pose); _nodes.push_back(plane);
   }
+  void _mirror_measurement(const Plane3d& m) { _measure = m; }   // value already stored on the device (Slam::refresh_plane_measurements)
   void set_measurement(const Plane3d& m) {                // Factor.h:206 (Mapping.cpp:603)
     _measure = m;
     if (_h) { Vector4d v = m.vector(); double a[4] = {v(0), v(1), v(2), v(3)}; detail::check(pus_set_measurement(_h, _id, a)); }
@@ -456,6 +457,35 @@ class Slam {
     s.step = ++_step; return s;
   }
   double chi2() { double c = 0; detail::check(pus_chi2(_h, &c)); return c; }       // Slam.cpp:266-268
+
+  // ---- not in iSAM: the two per-solve loops of Mapper_mono that otherwise round-trip through the host ----
+  // Mapper_mono::update_plane_measurement (Mapping.cpp:590-607) in one call: frames[f] = the frame's pose node,
+  // seg_ptr / segs = its ground_seg2d_lines (CSR), and for every kept observation its factor, frame index and
+  // plane row (good_plane_indices).  The factors' measurement() mirrors are refreshed.
+  void refresh_plane_measurements(const std::vector<Pose3d_Node*>& frames, const std::vector<int>& seg_ptr,
+                                  const std::vector<float>& segs, const float invK[9],
+                                  const std::vector<Pose3d_Plane3d_Factor*>& facs, const std::vector<int>& fac_frame,
+                                  const std::vector<int>& fac_row) {
+    std::vector<int> ids(frames.size()), fids(facs.size());
+    for (size_t i = 0; i < frames.size(); i++) ids[i] = frames[i]->unique_id();
+    for (size_t i = 0; i < facs.size(); i++) fids[i] = facs[i]->unique_id();
+    std::vector<double> m(4 * facs.size() + 4);
+    detail::check(pus_refresh_plane_measurements(_h, (int)frames.size(), ids.data(), seg_ptr.data(), segs.data(), invK, (int)facs.size(),
+                                                 fids.data(), fac_frame.data(), fac_row.data(), m.data()));
+    for (size_t i = 0; i < facs.size(); i++) {
+      Vector4d v; v(0) = m[4 * i]; v(1) = m[4 * i + 1]; v(2) = m[4 * i + 2]; v(3) = m[4 * i + 3];
+      facs[i]->_mirror_measurement(Plane3d(v));
+    }
+  }
+  // Plane3d::project_to_plane over all polygon vertices (Mapper_mono::reproj_to_newplane, Mapping.cpp:609-632):
+  // xyz[3*i..] is replaced by its projection onto the current estimate of planes[i]
+  void project_to_planes(const std::vector<Plane3d_Node*>& planes, std::vector<float>& xyz) {
+    std::vector<int> ids(planes.size());
+    for (size_t i = 0; i < planes.size(); i++) ids[i] = planes[i]->unique_id();
+    std::vector<float> out(xyz.size());
+    detail::check(pus_project_to_planes(_h, (int)planes.size(), ids.data(), xyz.data(), out.data()));
+    xyz.swap(out);
+  }
 };
 
 // aliases for BASELINE.json's g2o-flavoured vocabulary (no g2o code exists upstream)

@@ -199,6 +199,28 @@ int pus_popup_fit_frames(int device, int n_frames, const int* seg_ptr, const flo
                          const float* Ts, float dist_thre, int mode, float* planes_world, float* planes_sensor,
                          float* dist, int* good);
 
+/* ---- device-resident measurement refresh and polygon re-projection -------- */
+/* Mapper_mono::update_plane_measurement (pop_planar_slam/src/Mapping.cpp:590-607): after a solve every past
+ * frame re-pops its wall planes from its ground segments with the frame's LATEST pose estimate
+ * (popup_plane::update_plane_equation_from_seg, popup_plane.cpp:654-705, float32) and stores the sensor-frame
+ * plane of every kept observation as the new measurement of its pose-plane factor
+ * (Plane3d(Vector4d) normalisation, isam_plane3d.h:59-66; FactorT::set_measurement, Factor.h:203-206).
+ * Here the poses are read from the device-resident estimates of the last solve / upload (uploaded first if the
+ * graph is not resident), the fit and the factor store run on the device, and only the new measurements come
+ * back to refresh the host mirrors (pus_get_measurement):
+ *   frame_pose[n_frames]   pose node id of every frame
+ *   seg_ptr[n_frames+1], segs, invK   as pus_popup_fit_frames
+ *   map_fid / map_frame / map_row [n_map]   factor id, frame index, plane row inside the frame
+ *                                           (0 = ground, 1 + i = segment i: good_plane_indices)
+ *   new_meas[n_map*4]      optional copy of the stored measurements */
+int pus_refresh_plane_measurements(pus_handle h, int n_frames, const int* frame_pose, const int* seg_ptr,
+                                   const float* segs, const float* invK, int n_map, const int* map_fid,
+                                   const int* map_frame, const int* map_row, double* new_meas);
+/* Plane3d::project_to_plane (isam_plane3d.h:172-177) over point lists, as Mapper_mono::reproj_to_newplane
+ * applies it to every stored polygon vertex (Mapping.cpp:609-632): pts_out[i] = float(project(double(pts_in[i])))
+ * onto the current device-resident estimate of plane node plane_of_point[i]. */
+int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point, const float* pts_in, float* pts_out);
+
 /* ---- debug / test hooks ----------------------------------------------------------------- */
 /* copy a named device buffer of the last upload/solve to the host as doubles
  * ("Hpp","gp","Hll","gl","W","Wt","Hoff","Minv","delta", ...). Returns element count, <0 if unknown. */

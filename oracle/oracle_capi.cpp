@@ -325,4 +325,56 @@ int orc_popup_fit_frames(int, int n_frames, const int* seg_ptr, const float* seg
   return 0;
 }
 
+// Mapper_mono::update_plane_measurement  pop_planar_slam/src/Mapping.cpp:590-607
+//   for every frame: latest_pose = pose_vertex->value().wTo() cast to float (:598-599);
+//   update_plane_equation_from_seg(ground_seg2d_lines, inv_calib, pose, all_planes_sensor_new) (:600);
+//   for every kept plane: Plane3d(row.cast<double>()) (:602) -> pose_plane_facs[plane_id]->set_measurement (:603)
+int orc_refresh_plane_measurements(void* h, int n_frames, const int* frame_pose, const int* seg_ptr, const float* segs,
+                                   const float* invK, int n_map, const int* map_fid, const int* map_frame, const int* map_row,
+                                   double* new_meas) {
+  Slam* sl = S(h);
+  const int n_rows = seg_ptr[n_frames] + n_frames;
+  std::vector<float> ps((size_t)n_rows * 4, 0.f);
+  for (int f = 0; f < n_frames; f++) {
+    const int id = frame_pose[f];
+    if (id < 0 || id >= (int)sl->nodes.size() || !sl->nodes[id].alive || sl->nodes[id].kind != NODE_POSE) { g_err = "not a pose node"; return -1; }
+    double Td[16];
+    pose_wTo(sl->nodes[id].pose, Td);
+    float T[16];
+    for (int i = 0; i < 16; i++) T[i] = (float)Td[i];
+    const int s0 = seg_ptr[f], n = seg_ptr[f + 1] - s0;
+    if (n <= 0) continue;
+    popup_fit(segs + 4 * s0, n, invK, T, 0.f, 0, nullptr, ps.data() + 4 * (size_t)(s0 + f), nullptr, nullptr, nullptr, nullptr);
+  }
+  for (int m = 0; m < n_map; m++) {
+    const int f = map_frame[m], fid = map_fid[m];
+    if (fid < 0 || fid >= (int)sl->factors.size() || !sl->factors[fid].alive || sl->factors[fid].kind != F_POSE_PLANE) { g_err = "not a pose-plane factor"; return -1; }
+    const float* r = ps.data() + 4 * (size_t)(seg_ptr[f] + f + map_row[m]);
+    double v[4] = {(double)r[0], (double)r[1], (double)r[2], (double)r[3]};
+    sl->set_measurement(fid, v);
+    if (new_meas) std::memcpy(new_meas + 4 * (size_t)m, sl->factors[fid].meas, 4 * sizeof(double));
+  }
+  return 0;
+}
+
+// Plane3d::project_to_plane  PPS/src/isam_plane3d.h:172-177 (normal() :149-151, d() :154-156) as applied to the
+// polygon vertices by Mapper_mono::reproj_to_newplane, Mapping.cpp:609-632 (float -> double -> float)
+int orc_project_to_planes(void* h, int n_points, const int* plane_of_point, const float* in, float* out) {
+  Slam* sl = S(h);
+  for (int i = 0; i < n_points; i++) {
+    const int id = plane_of_point[i];
+    if (id < 0 || id >= (int)sl->nodes.size() || !sl->nodes[id].alive || sl->nodes[id].kind != NODE_PLANE) { g_err = "not a plane node"; return -1; }
+    const double* pl = sl->nodes[id].plane.v;
+    const double nn = std::sqrt(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2]);
+    const double nx = pl[0] / nn, ny = pl[1] / nn, nz = pl[2] / nn;
+    const double dd = -pl[3] / nn;
+    const double px = in[3 * (size_t)i], py = in[3 * (size_t)i + 1], pz = in[3 * (size_t)i + 2];
+    const double t = (nx * px + ny * py + nz * pz) - dd;
+    out[3 * (size_t)i] = (float)(px - nx * t);
+    out[3 * (size_t)i + 1] = (float)(py - ny * t);
+    out[3 * (size_t)i + 2] = (float)(pz - nz * t);
+  }
+  return 0;
+}
+
 }  // extern "C"

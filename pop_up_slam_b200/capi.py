@@ -284,6 +284,30 @@ class GraphAPI:
         n = min(n, cap)
         return dict(lam=lam[:n], chi2_new=en[:n], chi2_before=eb[:n], delta_norm=dn[:n], accepted=acc[:n], pcg=pcg[:n])
 
+    def refresh_plane_measurements(self, frame_pose, seg_ptr, segs, invK, map_fid, map_frame, map_row):
+        """Mapper_mono::update_plane_measurement on the resident estimates (include/popup_gpu.h); returns the new
+        measurements [n_map, 4]."""
+        frame_pose, seg_ptr = _i32(frame_pose), _i32(seg_ptr)
+        map_fid, map_frame, map_row = _i32(map_fid), _i32(map_frame), _i32(map_row)
+        segs = np.ascontiguousarray(segs, dtype=np.float32).reshape(-1, 4)
+        invK = np.ascontiguousarray(invK, dtype=np.float32).reshape(3, 3)
+        out = np.zeros((len(map_fid), 4))
+        fn = self._f("refresh_plane_measurements")
+        fn.argtypes = [C.c_void_p, C.c_int, c_int_p, c_int_p, c_float_p, c_float_p, C.c_int, c_int_p, c_int_p, c_int_p, c_double_p]
+        self._chk(fn(self.h, len(frame_pose), _ip(frame_pose), _ip(seg_ptr), segs.ctypes.data_as(c_float_p),
+                     invK.ctypes.data_as(c_float_p), len(map_fid), _ip(map_fid), _ip(map_frame), _ip(map_row), _dp(out)))
+        return out
+
+    def project_to_planes(self, plane_ids, pts):
+        """Plane3d::project_to_plane of float points onto the current plane estimates (include/popup_gpu.h)."""
+        plane_ids = _i32(plane_ids)
+        pts = np.ascontiguousarray(pts, dtype=np.float32).reshape(-1, 3)
+        out = np.zeros_like(pts)
+        fn = self._f("project_to_planes")
+        fn.argtypes = [C.c_void_p, C.c_int, c_int_p, c_float_p, c_float_p]
+        self._chk(fn(self.h, len(plane_ids), _ip(plane_ids), pts.ctypes.data_as(c_float_p), out.ctypes.data_as(c_float_p)))
+        return out
+
 
 class GpuGraphAPI(GraphAPI):
     """GraphAPI plus the entry points only the CUDA library has (solver options, split

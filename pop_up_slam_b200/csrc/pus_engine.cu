@@ -350,6 +350,10 @@ struct Solver {
   Compiled c;
   uint64_t compiled_topo = 0;
   bool meas_dirty = true;
+  void* scratch = nullptr;     // grow-only device scratch of the refresh / projection entry points
+  size_t scratch_bytes = 0;
+  std::vector<int> fid2slot;   // pose-plane factor id -> pose-major edge slot (built on demand)
+  uint64_t fid2slot_topo = 0;
   bool uploaded = false;
   int step = 0;
   cudaStream_t stream = nullptr;
@@ -668,6 +672,38 @@ using namespace pus;
 #define SV(h) (reinterpret_cast<Solver*>(h))
 #define NEED(h) if (!(h)) { g_err = "null handle"; return -1; }
 
+// launchers of pus_popup.cu (compiled without FMA contraction: float32 pop-up arithmetic as the reference's)
+namespace pus {
+cudaError_t launch_refresh(cudaStream_t st, int n_frames, const int* d_frame_pose, const double* d_pose7, const int* d_seg_ptr,
+                           const int* d_row_frame, int n_rows, const float* d_segs, const float* d_invK, float* d_Ts,
+                           float* d_planes_sensor, int n_map, const int* d_map_row, const int* d_map_slot, double* d_pp_meas,
+                           double* d_out);
+cudaError_t launch_project(cudaStream_t st, int n, const int* d_plane_idx, const double* d_plane4, const float* d_in, float* d_out);
+}  // namespace pus
+
+// scratch for the refresh / projection entry points: carved from one grow-only device buffer owned by the solver
+struct Scratch {
+  Solver* s;
+  cudaStream_t st;
+  size_t off = 0;
+  static size_t al(size_t b) { return (b + 255) / 256 * 256; }
+  bool reserve(size_t bytes) {
+    if (bytes <= s->scratch_bytes) return true;
+    if (s->scratch) { cudaStreamSynchronize(st); cudaFree(s->scratch); s->scratch = nullptr; s->scratch_bytes = 0; }
+    if (cudaMalloc(&s->scratch, bytes) != cudaSuccess) return false;
+    s->scratch_bytes = bytes;
+    return true;
+  }
+  template <typename T>
+  T* put(const T* host, size_t n) {   // carve (and fill when host != nullptr)
+    T* p = reinterpret_cast<T*>(static_cast<char*>(s->scratch) + off);
+    off += al(std::max<size_t>(n, 1) * sizeof(T));
+    if (off > s->scratch_bytes) return nullptr;
+    if (host && n && cudaMemcpyAsync(p, host, n * sizeof(T), cudaMemcpyHostToDevice, st) != cudaSuccess) return nullptr;
+    return p;
+  }
+};
+
 extern "C" {
 
 const char* pus_last_error(void) { return g_err.c_str(); }
@@ -686,6 +722,7 @@ int pus_destroy(pus_handle h) {
   Solver* s = SV(h);
   cudaSetDevice(s->device);
   s->free_device();
+  if (s->scratch) cudaFree(s->scratch);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
   if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
@@ -936,6 +973,103 @@ int pus_get_trace(pus_handle h, int cap, double* lambda, double* e_new, double* 
 }
 
 // ---- debug hooks ----
+// ---- device-resident measurement refresh / polygon re-projection ----
+int pus_refresh_plane_measurements(pus_handle h, int n_frames, const int* frame_pose, const int* seg_ptr, const float* segs,
+                                   const float* invK, int n_map, const int* map_fid, const int* map_frame, const int* map_row,
+                                   double* new_meas) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (n_frames <= 0) return 0;
+  if (!s->uploaded || s->compiled_topo != s->g.topo_version) {
+    if (upload(s) < 0) return -1;
+  } else if (ensure_device(s) < 0) {
+    return -1;
+  }
+  const Compiled& c = s->c;
+  const int n_seg = seg_ptr[n_frames], n_rows = n_seg + n_frames;
+  std::vector<int> fpose(n_frames), row_frame(n_rows), mrow(n_map), mslot(n_map);
+  for (int f = 0; f < n_frames; f++) {
+    if (!s->g.ok_node(frame_pose[f], NODE_POSE)) { g_err = "frame " + std::to_string(f) + ": not a pose node"; return -1; }
+    if (seg_ptr[f + 1] < seg_ptr[f]) { g_err = "seg_ptr must be non-decreasing"; return -1; }
+    fpose[f] = c.node_idx[frame_pose[f]];
+    for (int r = seg_ptr[f] + f; r < seg_ptr[f + 1] + f + 1; r++) row_frame[r] = f;
+  }
+  if ((int)s->fid2slot.size() != (int)s->g.factors.size() || s->fid2slot_topo != s->compiled_topo) {
+    s->fid2slot.assign(s->g.factors.size(), -1);
+    for (int e = 0; e < c.nslot; e++) if (c.pp_fid[e] >= 0) s->fid2slot[c.pp_fid[e]] = e;
+    s->fid2slot_topo = s->compiled_topo;
+  }
+  for (int m = 0; m < n_map; m++) {
+    const int f = map_frame[m], fid = map_fid[m];
+    if (f < 0 || f >= n_frames) { g_err = "map_frame out of range"; return -1; }
+    const int ns = seg_ptr[f + 1] - seg_ptr[f];
+    if (ns <= 0 || map_row[m] < 0 || map_row[m] > ns) { g_err = "map_row out of range (frames without segments produce no planes)"; return -1; }
+    if (!s->g.ok_factor(fid) || s->g.factors[fid].kind != F_POSE_PLANE || s->fid2slot[fid] < 0) { g_err = "map_fid is not a pose-plane factor"; return -1; }
+    mrow[m] = seg_ptr[f] + f + map_row[m];
+    mslot[m] = s->fid2slot[fid];
+  }
+  CUDA_OK(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  Scratch sc{s, st};
+  if (!sc.reserve(Scratch::al(4 * (size_t)n_frames) + Scratch::al(4 * (size_t)(n_frames + 1)) + Scratch::al(4 * (size_t)n_rows) +
+                  Scratch::al(16 * (size_t)std::max(n_seg, 1)) + Scratch::al(36) + 2 * Scratch::al(4 * (size_t)std::max(n_map, 1)) +
+                  Scratch::al(64 * (size_t)n_frames) + Scratch::al(16 * (size_t)n_rows) + Scratch::al(32 * (size_t)std::max(n_map, 1)))) {
+    g_err = "scratch allocation failed";
+    return -1;
+  }
+  int* d_fpose = sc.put(fpose.data(), n_frames);
+  int* d_ptr = sc.put(seg_ptr, n_frames + 1);
+  int* d_rf = sc.put(row_frame.data(), n_rows);
+  float* d_segs = sc.put(segs, (size_t)n_seg * 4);
+  float* d_K = sc.put(invK, 9);
+  int* d_mrow = sc.put(mrow.data(), n_map);
+  int* d_mslot = sc.put(mslot.data(), n_map);
+  float* d_T = sc.put<float>(nullptr, (size_t)n_frames * 16);
+  float* d_ps = sc.put<float>(nullptr, (size_t)n_rows * 4);
+  double* d_out = sc.put<double>(nullptr, (size_t)n_map * 4);
+  if (!d_fpose || !d_ptr || !d_rf || !d_segs || !d_K || !d_mrow || !d_mslot || !d_T || !d_ps || !d_out) { g_err = "scratch allocation failed"; return -1; }
+  CUDA_OK(cudaMemsetAsync(d_ps, 0, (size_t)n_rows * 4 * sizeof(float), st));
+  CUDA_OK(launch_refresh(st, n_frames, d_fpose, s->hd.pose_lin, d_ptr, d_rf, n_rows, d_segs, d_K, d_T, d_ps, n_map, d_mrow, d_mslot,
+                         const_cast<double*>(s->hd.pp_meas), d_out));
+  std::vector<double> out((size_t)n_map * 4);
+  if (n_map) CUDA_OK(cudaMemcpyAsync(out.data(), d_out, out.size() * 8, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  for (int m = 0; m < n_map; m++) {   // host mirrors: the factor store and the compiled copy
+    std::memcpy(s->g.factors[map_fid[m]].meas, &out[(size_t)m * 4], 4 * sizeof(double));
+    std::memcpy(&s->c.pp_meas[(size_t)mslot[m] * 4], &out[(size_t)m * 4], 4 * sizeof(double));
+  }
+  if (new_meas && n_map) std::memcpy(new_meas, out.data(), out.size() * 8);
+  return 0;
+}
+
+int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point, const float* pts_in, float* pts_out) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (n_points <= 0) return 0;
+  if (!s->uploaded || s->compiled_topo != s->g.topo_version) {
+    if (upload(s) < 0) return -1;
+  } else if (ensure_device(s) < 0) {
+    return -1;
+  }
+  std::vector<int> idx(n_points);
+  for (int i = 0; i < n_points; i++) {
+    if (!s->g.ok_node(plane_of_point[i], NODE_PLANE)) { g_err = "point " + std::to_string(i) + ": not a plane node"; return -1; }
+    idx[i] = s->c.node_idx[plane_of_point[i]];
+  }
+  CUDA_OK(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  Scratch sc{s, st};
+  if (!sc.reserve(Scratch::al(4 * (size_t)n_points) + 2 * Scratch::al(12 * (size_t)n_points))) { g_err = "scratch allocation failed"; return -1; }
+  int* d_idx = sc.put(idx.data(), n_points);
+  float* d_in = sc.put(pts_in, (size_t)n_points * 3);
+  float* d_out = sc.put<float>(nullptr, (size_t)n_points * 3);
+  if (!d_idx || !d_in || !d_out) { g_err = "scratch allocation failed"; return -1; }
+  CUDA_OK(launch_project(st, n_points, d_idx, s->hd.plane_lin, d_in, d_out));
+  CUDA_OK(cudaMemcpyAsync(pts_out, d_out, (size_t)n_points * 3 * sizeof(float), cudaMemcpyDeviceToHost, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  return 0;
+}
+
 long long pus_debug_fetch(pus_handle h, const char* name, double* out, long long cap) {
   NEED(h);
   Solver* s = SV(h);

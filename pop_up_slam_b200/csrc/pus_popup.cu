@@ -99,6 +99,71 @@ __global__ void popup_kernel(int n_frames, const int* __restrict__ seg_ptr, cons
     }
   }
 }
+// ---- device-resident refresh (pus_refresh_plane_measurements) -------------------------------------------
+// Pose3d::wTo (Pose3d.h:188-194) of the frame's pose estimate, cast to float as Mapping.cpp:598-599 does
+__global__ void frame_pose_kernel(int n_frames, const int* __restrict__ frame_pose, const double* pose7, float* Ts) {
+  int f = blockIdx.x * blockDim.x + threadIdx.x;
+  if (f >= n_frames) return;
+  const double* p = pose7 + (size_t)frame_pose[f] * 7;
+  const double qw = p[3], qx = p[4], qy = p[5], qz = p[6];
+  // Eigen toRotationMatrix, no normalisation (Rot3d.h:96-98)
+  const double tx = 2 * qx, ty = 2 * qy, tz = 2 * qz;
+  const double twx = tx * qw, twy = ty * qw, twz = tz * qw;
+  const double txx = tx * qx, txy = ty * qx, txz = tz * qx;
+  const double tyy = ty * qy, tyz = tz * qy, tzz = tz * qz;
+  float* T = Ts + (size_t)f * 16;
+  T[0] = (float)(1 - (tyy + tzz)); T[1] = (float)(txy - twz);       T[2] = (float)(txz + twy);        T[3] = (float)p[0];
+  T[4] = (float)(txy + twz);       T[5] = (float)(1 - (txx + tzz)); T[6] = (float)(tyz - twx);        T[7] = (float)p[1];
+  T[8] = (float)(txz - twy);       T[9] = (float)(tyz + twx);       T[10] = (float)(1 - (txx + tyy)); T[11] = (float)p[2];
+  T[12] = 0.f; T[13] = 0.f; T[14] = 0.f; T[15] = 1.f;
+}
+
+// Plane3d(row.cast<double>()) (normalised 4-vector) -> the factor's measurement slot and the host copy
+__global__ void store_meas_kernel(int n_map, const int* __restrict__ map_row, const int* __restrict__ map_slot,
+                                  const float* __restrict__ planes_sensor, double* pp_meas, double* out) {
+  int m = blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= n_map) return;
+  const float* r = planes_sensor + (size_t)map_row[m] * 4;
+  double v[4] = {(double)r[0], (double)r[1], (double)r[2], (double)r[3]};
+  const double z = v[0] * v[0] + v[1] * v[1] + v[2] * v[2] + v[3] * v[3];
+  if (z > 0) {
+    const double n = sqrt(z);
+    v[0] /= n; v[1] /= n; v[2] /= n; v[3] /= n;
+  }
+  double* dst = pp_meas + (size_t)map_slot[m] * 4;
+  for (int i = 0; i < 4; i++) { dst[i] = v[i]; out[(size_t)m * 4 + i] = v[i]; }
+}
+
+// Plane3d::project_to_plane (isam_plane3d.h:172-177): normal() = abc/|abc|, d() = -d/|abc|
+__global__ void project_kernel(int n, const int* __restrict__ plane_idx, const double* plane4, const float* __restrict__ in, float* out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double* pl = plane4 + (size_t)plane_idx[i] * 4;
+  const double nn = sqrt(pl[0] * pl[0] + pl[1] * pl[1] + pl[2] * pl[2]);
+  const double nx = pl[0] / nn, ny = pl[1] / nn, nz = pl[2] / nn;
+  const double dd = -pl[3] / nn;
+  const double px = in[(size_t)i * 3], py = in[(size_t)i * 3 + 1], pz = in[(size_t)i * 3 + 2];
+  const double t = (nx * px + ny * py + nz * pz) - dd;
+  out[(size_t)i * 3] = (float)(px - nx * t);
+  out[(size_t)i * 3 + 1] = (float)(py - ny * t);
+  out[(size_t)i * 3 + 2] = (float)(pz - nz * t);
+}
+
+// launchers used by pus_engine.cu (all pointers are device pointers)
+cudaError_t launch_refresh(cudaStream_t st, int n_frames, const int* d_frame_pose, const double* d_pose7, const int* d_seg_ptr,
+                           const int* d_row_frame, int n_rows, const float* d_segs, const float* d_invK, float* d_Ts,
+                           float* d_planes_sensor, int n_map, const int* d_map_row, const int* d_map_slot, double* d_pp_meas,
+                           double* d_out) {
+  frame_pose_kernel<<<(n_frames + 127) / 128, 128, 0, st>>>(n_frames, d_frame_pose, d_pose7, d_Ts);
+  popup_kernel<<<(n_rows + 255) / 256, 256, 0, st>>>(n_frames, d_seg_ptr, d_row_frame, n_rows, d_segs, d_invK, d_Ts, 0.f, 0, nullptr,
+                                                      d_planes_sensor, nullptr, nullptr);
+  if (n_map > 0) store_meas_kernel<<<(n_map + 255) / 256, 256, 0, st>>>(n_map, d_map_row, d_map_slot, d_planes_sensor, d_pp_meas, d_out);
+  return cudaGetLastError();
+}
+cudaError_t launch_project(cudaStream_t st, int n, const int* d_plane_idx, const double* d_plane4, const float* d_in, float* d_out) {
+  project_kernel<<<(n + 255) / 256, 256, 0, st>>>(n, d_plane_idx, d_plane4, d_in, d_out);
+  return cudaGetLastError();
+}
 }  // namespace pus
 
 using namespace pus;

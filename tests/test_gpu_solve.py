@@ -297,6 +297,56 @@ def test_popup_fit_matches_oracle():
             assert np.array_equal(a, b)   # float32, same operation order, no FMA contraction: bit-exact
 
 
+def test_measurement_refresh_and_reprojection_match_oracle():
+    """SURVEY 8f.1: Mapper_mono::update_plane_measurement / reproj_to_newplane on the device-resident estimates.
+    After a solve every frame re-pops its planes with its latest pose and the kept observations become the new
+    factor measurements; then another solve.  Measurements, the second solve and the polygon re-projection follow
+    the oracle's restatement of Mapping.cpp:590-632 (float32 pop-up arithmetic; 1e-5 on the stored measurements)."""
+    g = gg.make_config(2, seed=5, n_poses=80, n_planes=20)
+    rng = np.random.default_rng(11)
+    nf = g.n_poses
+    nseg = rng.integers(0, 6, size=nf)
+    seg_ptr = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int32)
+    segs = np.stack([rng.uniform(0, 640, seg_ptr[-1]), rng.uniform(300, 480, seg_ptr[-1]),
+                     rng.uniform(0, 640, seg_ptr[-1]), rng.uniform(300, 480, seg_ptr[-1])], axis=1).astype(np.float32)
+    K = np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]])
+    invK = np.linalg.inv(K).astype(np.float32)
+    # every pose-plane factor of a frame with segments is re-measured from one of that frame's rows
+    order = np.argsort(g.pp_pose, kind="stable")
+    mf, mr, me = [], [], []
+    for e in order:
+        f = int(g.pp_pose[e])
+        if nseg[f] > 0:
+            mf.append(f); mr.append(int(rng.integers(0, nseg[f] + 1))); me.append(int(e))
+    pts = rng.uniform(-5, 5, size=(500, 3)).astype(np.float32)
+    res = []
+    for api in (GpuGraphAPI(), OracleAPI()):
+        if isinstance(api, OracleAPI):
+            api.set_jacobian_mode(1)
+        info = gg.build_bulk(api, g)
+        gg.configure(api, g)
+        api.batch_optimize()
+        pl_ids = info["plane_ids"][np.arange(len(pts)) % g.n_planes]
+        proj = api.project_to_planes(pl_ids, pts)
+        L = api.get_planes(pl_ids)                 # the kernel against numpy on the API's own plane estimates
+        nn = np.linalg.norm(L[:, :3], axis=1)
+        nrm = L[:, :3] / nn[:, None]
+        ref = pts.astype(np.float64) - nrm * ((nrm * pts).sum(axis=1) + L[:, 3] / nn)[:, None]
+        assert np.abs(proj - ref.astype(np.float32)).max() <= 2e-6 * max(1.0, np.abs(ref).max())
+        new = api.refresh_plane_measurements(info["pose_ids"], seg_ptr, segs, invK, info["pp_fids"][me], mf, mr)
+        got = np.array([api.get_measurement(int(fid))[:4] for fid in info["pp_fids"][me]])
+        assert np.array_equal(new, got)            # host mirrors refreshed
+        it2 = api.batch_optimize()                 # the next solve uses the refreshed measurements
+        res.append((new, it2, api.chi2(), api.get_poses(info["pose_ids"]), proj, info))
+    (n_g, it_g, c_g, P_g, pr_g, ig), (n_o, it_o, c_o, P_o, pr_o, io) = res
+    assert np.isfinite(n_o).all()
+    assert np.abs(n_g - n_o).max() <= 1e-5
+    assert it_g == it_o
+    assert abs(c_g - c_o) <= 1e-4 * abs(c_o)
+    assert np.abs(P_g[:, :3] - P_o[:, :3]).max() <= 1e-4 * max(1.0, np.abs(P_o[:, :3]).max())
+    assert np.abs(pr_g - pr_o).max() <= 1e-5 * max(1.0, np.abs(pr_o).max())
+
+
 def test_gpu_matches_frozen_goldens():
     """the committed oracle outputs (tests/golden, numeric Jacobians as the reference) without running the oracle"""
     import json

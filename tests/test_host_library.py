@@ -137,3 +137,8 @@ def test_no_cpu_fallback_without_a_gpu():
             call()
     with pytest.raises(capi.ApiError):
         capi.popup_fit_frames(a.lib, [0, 1], np.zeros((1, 4), np.float32), np.eye(3, dtype=np.float32), np.eye(4, dtype=np.float32)[None])
+    ids = gg.build_bulk(GpuGraphAPI(), g)   # (ids are deterministic: same as the graph above)
+    with pytest.raises(capi.ApiError, match="no CUDA device|CUDA"):
+        a.refresh_plane_measurements(ids["pose_ids"][:1], [0, 1], np.zeros((1, 4), np.float32), np.eye(3), ids["pp_fids"][:1], [0], [0])
+    with pytest.raises(capi.ApiError, match="no CUDA device|CUDA"):
+        a.project_to_planes(ids["plane_ids"][:1], np.zeros((1, 3), np.float32))

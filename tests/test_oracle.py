@@ -189,3 +189,38 @@ def test_sphere400_reference_dataset():
     c1 = api.chi2()
     assert c1 < 1e-2 * c0
     assert c1 / (6 * n_edges + 6 - 6 * 400) < 5.0      # normalised chi2 of a converged sphere400 is O(1)
+
+
+def test_measurement_refresh_and_projection_geometry():
+    """the oracle's restatement of Mapper_mono::update_plane_measurement / reproj_to_newplane (Mapping.cpp:590-632)
+    against independent numpy geometry: the ground row of a frame is normalize(wTo^T (0,0,-1,0)); a wall row contains
+    the two ground points its segment pops up from; projected points lie on the plane and move along its normal."""
+    g = gg.make_config(2, seed=3, n_poses=30, n_planes=10)
+    o = OracleAPI()
+    ids = gg.build_bulk(o, g)
+    rng = np.random.default_rng(2)
+    K = np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]])
+    invK = np.linalg.inv(K)
+    order = np.argsort(g.pp_pose, kind="stable")
+    e0, e1 = int(order[0]), int(order[1])          # two factors of pose 0
+    f = int(g.pp_pose[e0])
+    segs = np.array([[100.0, 400.0, 500.0, 380.0]], dtype=np.float32)
+    new = o.refresh_plane_measurements([ids["pose_ids"][f]], [0, 1], segs, invK, ids["pp_fids"][[e0, e1]], [0, 0], [0, 1])
+    T = geo.pose7_to_T(o.get_pose(int(ids["pose_ids"][f])))
+    ground = T.T @ np.array([0, 0, -1.0, 0])
+    assert np.allclose(new[0], ground / np.linalg.norm(ground), atol=1e-6)
+    # wall plane (sensor frame) contains the back-projected ground points of both segment ends
+    gs = ground
+    for px, py in ((100.0, 400.0), (500.0, 380.0)):
+        ray = invK @ np.array([px, py, 1.0])
+        P = -gs[3] / (gs[:3] @ ray) * ray
+        assert abs(new[1][:3] @ P + new[1][3]) <= 1e-4
+    assert np.allclose(o.get_measurement(int(ids["pp_fids"][e1])), new[1])
+    pts = rng.uniform(-3, 3, size=(50, 3)).astype(np.float32)
+    pl = ids["plane_ids"][np.arange(50) % g.n_planes]
+    pr = o.project_to_planes(pl, pts)
+    for i in range(50):
+        v = o.get_plane(int(pl[i]))
+        n = v[:3] / np.linalg.norm(v[:3])
+        assert abs(n @ pr[i] + v[3] / np.linalg.norm(v[:3])) <= 1e-5
+        assert np.linalg.norm(np.cross(pr[i] - pts[i], n)) <= 1e-5
