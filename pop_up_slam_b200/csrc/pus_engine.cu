@@ -358,7 +358,6 @@ struct Solver {
   int step = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
-  std::vector<void*> allocs;
   std::map<std::string, std::pair<double*, size_t>> named;  // debug access to double buffers
   DevGraph hd;
   DevGraph* d_graph = nullptr;
@@ -385,19 +384,39 @@ struct Solver {
   }
   int trace_n;
 
+  // Device buffers are recycled across topology changes: the n-th allocation of a rebuild re-uses the n-th buffer of
+  // the previous one when it is large enough (grown by 1.5x otherwise), so the frame-by-frame use of the reference
+  // (one structural edit per key-frame, Mapping.cpp:464-554) does not pay ~70 cudaFree + cudaMalloc per frame.
+  struct Slot { void* p; size_t cap; };
+  std::vector<Slot> pool;
+  size_t pool_next = 0;
   void free_device() {
-    for (void* p : allocs) cudaFree(p);
-    allocs.clear();
+    for (Slot& sl : pool) cudaFree(sl.p);
+    pool.clear();
+    recycle_device();
+  }
+  void recycle_device() {
+    pool_next = 0;
     named.clear();
     uploaded = false;
     compiled_topo = 0;
   }
   template <typename T>
   int dalloc(T** out, size_t n, const char* name = nullptr) {
-    void* p = nullptr;
-    size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
-    CUDA_OK(cudaMalloc(&p, bytes));
-    allocs.push_back(p);
+    const size_t bytes = std::max<size_t>(n, 1) * sizeof(T);
+    if (pool_next == pool.size()) {
+      void* p = nullptr;
+      CUDA_OK(cudaMalloc(&p, bytes));
+      pool.push_back(Slot{p, bytes});
+    } else if (pool[pool_next].cap < bytes) {
+      cudaFree(pool[pool_next].p);
+      pool[pool_next].p = nullptr; pool[pool_next].cap = 0;
+      const size_t cap = bytes + bytes / 2;
+      void* p = nullptr;
+      CUDA_OK(cudaMalloc(&p, cap));
+      pool[pool_next] = Slot{p, cap};
+    }
+    void* p = pool[pool_next++].p;
     *out = reinterpret_cast<T*>(p);
     if (name) named[name] = std::make_pair(reinterpret_cast<double*>(p), n);
     return 0;
@@ -445,7 +464,7 @@ static int upload(Solver* s) {
   CUDA_OK(cudaEventRecord(e0, s->stream));
   const bool rebuild = (s->compiled_topo != s->g.topo_version) || !s->uploaded;
   if (rebuild) {
-    s->free_device();
+    s->recycle_device();
     std::string err;
     if (!compile_graph(s->g, s->c, err)) { g_err = err; return -1; }
     const Compiled& c = s->c;
