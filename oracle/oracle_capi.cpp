@@ -1,7 +1,8 @@
 // ORACLE (test infrastructure, NOT product code) -- see oracle_math.hpp header.
 // C entry points (orc_*) with the same shapes as include/popup_gpu.h (pus_*), so the
 // parity tests can drive the oracle and the CUDA library through one Python wrapper.
-// "parity unpinned": no reference goldens exist for this path.
+// Parity: pose-graph path pinned against the reference's sphere2500 dataset + ground truth; plane path
+// "parity unpinned" (oracle_math.hpp).
 #include <cstring>
 #include <string>
 #include <vector>

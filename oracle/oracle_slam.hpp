@@ -2,7 +2,8 @@
 //
 // Restatement of the iSAM graph container, linearisation, direct solve and the
 // Gauss-Newton / Levenberg-Marquardt drivers exactly as pop_planar_slam uses them.
-// "parity unpinned" (no reference goldens exist; see oracle_math.hpp).
+// Parity: pose-graph path pinned against the reference's sphere2500 dataset + ground truth, plane path
+// "parity unpinned" (see oracle_math.hpp).
 //
 // Reference files followed (relative to /root/reference, ISAM = pop_planar_slam/Thirdparty/isam):
 //   ISAM/isamlib/Slam.cpp:59-67,91-126,157-210,216-268,395-432

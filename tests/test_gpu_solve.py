@@ -369,3 +369,25 @@ def test_gpu_matches_frozen_goldens():
         L, Lg = a.get_planes(ids["plane_ids"]), np.array(gold["planes"])
         sgn = np.sign(np.sum(L * Lg, axis=1))[:, None]
         assert np.abs(L * sgn - Lg).max() <= TOL
+
+
+def test_reference_sphere400_dataset_fixture():
+    """the reference's own pose-graph dataset (ISAM/data/sphere400.txt, committed as tests/golden/sphere400.json by
+    tools/make_sphere_golden.py together with the oracle's Gauss-Newton result): same iterations, chi2 and poses."""
+    import json, os, sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    sys.path.insert(0, os.path.join(os.path.dirname(here), "tools"))
+    from make_sphere_golden import build
+    fx = json.load(open(os.path.join(here, "golden", "sphere400.json")))
+    edges = [(int(e[0]), int(e[1]), e[2:8], e[8:29]) for e in fx["edges"]]
+    gpu = GpuGraphAPI()
+    gpu.set_properties(**fx["properties"])
+    ids = build(gpu, edges)
+    assert abs(gpu.chi2() - fx["oracle"]["chi2_initial"]) <= 1e-9 * fx["oracle"]["chi2_initial"]
+    assert gpu.batch_optimize() == fx["oracle"]["iterations"]
+    assert abs(gpu.chi2() - fx["oracle"]["chi2_final"]) <= TOL * fx["oracle"]["chi2_final"]
+    P = gpu.get_poses(np.array([ids[k] for k in fx["oracle"]["pose_index"]]))
+    Po = np.array(fx["oracle"]["poses"])
+    assert np.abs(P[:, :3] - Po[:, :3]).max() <= TOL * max(1.0, np.abs(Po[:, :3]).max())
+    sq = np.sign(np.sum(P[:, 3:] * Po[:, 3:], axis=1))[:, None]
+    assert np.abs(P[:, 3:] * sq - Po[:, 3:]).max() <= TOL

@@ -4,6 +4,7 @@ ground truth, chi2 monotonicity, the frozen goldens, and the reference's own ISA
 reference checkout is present."""
 import json
 import os
+import sys
 
 import numpy as np
 import pytest
@@ -224,3 +225,60 @@ def test_measurement_refresh_and_projection_geometry():
         n = v[:3] / np.linalg.norm(v[:3])
         assert abs(n @ pr[i] + v[3] / np.linalg.norm(v[:3])) <= 1e-5
         assert np.linalg.norm(np.cross(pr[i] - pts[i], n)) <= 1e-5
+
+
+SPHERE2500 = "/root/reference/pop_planar_slam/Thirdparty/isam/data/sphere2500.txt"
+SPHERE2500_GT = "/root/reference/pop_planar_slam/Thirdparty/isam/data/groundtruth/sphere2500_groundtruth.txt"
+
+
+@pytest.mark.skipif(not os.path.exists(SPHERE2500_GT), reason="reference checkout not present")
+def test_sphere2500_ground_truth_pins_the_pose_graph_path():
+    """Known answers held by the reference itself (ISAM/data/sphere2500.txt and data/groundtruth/):
+    (1) chaining the ground-truth file's sequential edges through the factors' initialize() path (oplus) must make
+        ALL of its 4 949 edges consistent, the 2 450 loop closures included: chi2 of the ground-truth graph ~ 0
+        (6-digit text rounding).  Any wrong convention in Pose3d (Euler order, oplus / ominus direction, the Loader's
+        roll-pitch-yaw swap) breaks this.
+    (2) Gauss-Newton on the noisy dataset must reach a normalised chi2 of 1 (the noise was drawn from the stated
+        sqrt-information) and land within 2 % of the sphere radius of the ground-truth trajectory."""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_sphere_golden import build, load_edge3
+    gt, noisy = load_edge3(SPHERE2500_GT), load_edge3(SPHERE2500)
+    assert len(gt) == len(noisy) == 4949
+    a = OracleAPI()
+    a.set_jacobian_mode(1)
+    ida = build(a, gt)
+    assert len(ida) == 2500
+    assert a.chi2() < 1e-2                                    # 29 700 weighted residual rows, weights 10 / 100 / 25
+    P_gt = a.get_poses(np.array([ida[k] for k in sorted(ida)]))
+    b = OracleAPI()
+    b.set_jacobian_mode(1)
+    b.set_properties(**dict(gg.PPS_PROPERTIES, method=0, max_iterations=20, epsilon_abs=1e-6, epsilon_rel=1e-8))
+    idb = build(b, noisy)
+    c0 = b.chi2()
+    b.batch_optimize()
+    c1 = b.chi2()
+    dof = 6 * len(noisy) + 6 - 6 * len(idb)
+    assert c1 < 1e-3 * c0
+    assert 0.95 < c1 / dof < 1.05
+    P = b.get_poses(np.array([idb[k] for k in sorted(idb)]))
+    err = np.linalg.norm(P[:, :3] - P_gt[:, :3], axis=1)
+    assert err.mean() < 0.02 * np.abs(P_gt[:, :3]).max()
+
+
+def test_oracle_matches_sphere400_fixture():
+    """the committed fixture of the reference's sphere400 dataset (tools/make_sphere_golden.py): the oracle still
+    produces the frozen Gauss-Newton result (numeric Jacobians as upstream)."""
+    import json
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    from make_sphere_golden import build
+    fx = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sphere400.json")))
+    edges = [(int(e[0]), int(e[1]), e[2:8], e[8:29]) for e in fx["edges"]]
+    api = OracleAPI()
+    api.set_jacobian_mode(0)
+    api.set_properties(**fx["properties"])
+    ids = build(api, edges)
+    assert abs(api.chi2() - fx["oracle"]["chi2_initial"]) <= 1e-9 * fx["oracle"]["chi2_initial"]
+    assert api.batch_optimize() == fx["oracle"]["iterations"]
+    assert abs(api.chi2() - fx["oracle"]["chi2_final"]) <= 1e-8 * fx["oracle"]["chi2_final"]
+    P = api.get_poses(np.array([ids[k] for k in fx["oracle"]["pose_index"]]))
+    assert np.abs(P - np.array(fx["oracle"]["poses"])).max() <= 1e-8
