@@ -143,6 +143,16 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
     return;
   }
   if (P.mode == MODE_DEBUG) {
+    if (P.debug_stage == 9) {   // micro-benchmark: 1000 team barriers, 1000 team reductions (phase_ms[0], [1])
+      tm.sync();
+      for (int i = 0; i < 1000; i++) team_barrier(c);
+      tm.lap(0);
+      double v[1] = {1.0};
+      for (int i = 0; i < 1000; i++) { v[0] = 1.0; team_reduce<1>(c, G.red, v); }
+      tm.lap(1);
+      if (lead) tm.flush(res);
+      return;
+    }
     if (P.debug_stage == 3) {  // q = S * pv[0] with the current linearisation / Schur set-up
       ph.sweep_planes(G.pv[0], nullptr, 0.0);
       team_barrier(c);
