@@ -457,6 +457,7 @@ class Slam {
     s.step = ++_step; return s;
   }
   double chi2() { double c = 0; detail::check(pus_chi2(_h, &c)); return c; }       // Slam.cpp:266-268
+  void save(const std::string& fname) const { detail::check(pus_save_graph(_h, fname.c_str(), 0)); }   // Slam.cpp:84-89
 
   // ---- not in iSAM: the two per-solve loops of Mapper_mono that otherwise round-trip through the host ----
   // Mapper_mono::update_plane_measurement (Mapping.cpp:590-607) in one call: frames[f] = the frame's pose node,

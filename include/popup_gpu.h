@@ -221,6 +221,20 @@ int pus_refresh_plane_measurements(pus_handle h, int n_frames, const int* frame_
  * onto the current device-resident estimate of plane node plane_of_point[i]. */
 int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point, const float* pts_in, float* pts_out);
 
+/* ---- graph text I/O (host only) ---------------------------------------------- */
+/* Slam::save (ISAM/isamlib/Slam.cpp:84-89 -> Graph::write, Graph.h:120-131): every factor, then every node, one per
+ * line: "<Factor name> <node ids> <measure> {sqrtinf upper triangle, row-wise, comma separated}" (Factor.h:148-155,
+ * 169-190, 208-211) and "<Type>_Node <id> <value>" (Node.h:148-153); Pose3d prints "(x, y, z; yaw, pitch, roll)"
+ * (Pose3d.h:169-172), Plane3d "(a, b, c; d)" (isam_plane3d.h:190-192).  The plane prior keeps the reference's
+ * name "Pose3d_Factor" (isam_plane3d.h:438).  precision <= 0 = the stream default of the reference (6 digits). */
+int pus_save_graph(pus_handle h, const char* path, int precision);
+/* The 3-D part of the iSAM dataset grammar (ISAM/isam/Loader.cpp:316-392): EDGE3 i j x y z roll pitch yaw [21
+ * sqrt-information entries, rotational block re-ordered] with the reversal of edges that point backwards and the
+ * 100*I prior on the first pose (Loader.cpp:48-64), POSE3D_INIT; EDGE3_INIT / POSE3D_TRUE / EDGE3_TRUE / SOLVE are
+ * skipped as upstream; the 2-D and stereo keywords are rejected.  Nodes are left to the factors' initialize().
+ * n_poses / n_factors (optional) receive what was added. */
+int pus_load_isam_dataset(pus_handle h, const char* path, int* n_poses, int* n_factors);
+
 /* ---- debug / test hooks ----------------------------------------------------------------- */
 /* copy a named device buffer of the last upload/solve to the host as doubles
  * ("Hpp","gp","Hll","gl","W","Wt","Hoff","Minv","delta", ...). Returns element count, <0 if unknown. */

@@ -284,6 +284,20 @@ class GraphAPI:
         n = min(n, cap)
         return dict(lam=lam[:n], chi2_new=en[:n], chi2_before=eb[:n], delta_norm=dn[:n], accepted=acc[:n], pcg=pcg[:n])
 
+    def save_graph(self, path, precision=0):
+        """Slam::save text format (include/popup_gpu.h); host only."""
+        fn = self._f("save_graph")
+        fn.argtypes = [C.c_void_p, C.c_char_p, C.c_int]
+        self._chk(fn(self.h, str(path).encode(), int(precision)))
+
+    def load_isam_dataset(self, path):
+        """3-D part of the iSAM dataset grammar (EDGE3, POSE3D_INIT); returns (poses added, factors added)."""
+        fn = self._f("load_isam_dataset")
+        fn.argtypes = [C.c_void_p, C.c_char_p, c_int_p, c_int_p]
+        a, b = C.c_int(0), C.c_int(0)
+        self._chk(fn(self.h, str(path).encode(), C.byref(a), C.byref(b)))
+        return a.value, b.value
+
     def refresh_plane_measurements(self, frame_pose, seg_ptr, segs, invK, map_fid, map_frame, map_row):
         """Mapper_mono::update_plane_measurement on the resident estimates (include/popup_gpu.h); returns the new
         measurements [n_map, 4]."""

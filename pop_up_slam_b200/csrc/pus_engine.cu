@@ -1099,6 +1099,141 @@ int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point,
   return 0;
 }
 
+// ---- graph text I/O (host only) ----
+int pus_save_graph(pus_handle h, const char* path, int precision) {
+  NEED(h);
+  Solver* s = SV(h);
+  FILE* fp = std::fopen(path, "wb");
+  if (!fp) { g_err = std::string("pus_save_graph: cannot open ") + path; return -1; }
+  const int prec = precision > 0 ? precision : 6;
+  auto num = [&](double v) { char b[64]; std::snprintf(b, sizeof b, "%.*g", prec, v); return std::string(b); };
+  auto pose_str = [&](const double* p7) {   // Pose3d::write, Pose3d.h:169-172
+    double yaw, pitch, roll;
+    quat_to_euler(p7 + 3, yaw, pitch, roll);
+    return "(" + num(p7[0]) + ", " + num(p7[1]) + ", " + num(p7[2]) + "; " + num(yaw) + ", " + num(pitch) + ", " + num(roll) + ")";
+  };
+  auto xyzypr_str = [&](const double* m) {
+    return "(" + num(m[0]) + ", " + num(m[1]) + ", " + num(m[2]) + "; " + num(m[3]) + ", " + num(m[4]) + ", " + num(m[5]) + ")";
+  };
+  auto plane_str = [&](const double* v) { return "(" + num(v[0]) + ", " + num(v[1]) + ", " + num(v[2]) + "; " + num(v[3]) + ")"; };
+  static const char* kFactorName[4] = {"Pose3d_Factor", "Pose3d_Pose3d_Factor", "Pose3d_Plane3d_Factor", "Pose3d_Factor"};
+  for (size_t f = 0; f < s->g.factors.size(); f++) {   // Graph::write: factors first (Graph.h:121-125)
+    const HFactor& F = s->g.factors[f];
+    if (!F.alive) continue;
+    std::string line = kFactorName[F.kind];
+    for (int i = 0; i < F.n_nodes; i++) line += " " + std::to_string(F.nodes[i]);
+    line += " " + (F.dim == 3 ? plane_str(F.meas) : xyzypr_str(F.meas)) + " {";
+    const int ne = F.dim * (F.dim + 1) / 2;
+    for (int i = 0; i < ne; i++) line += (i ? "," : "") + num(F.sinf[i]);
+    line += "}\n";
+    std::fputs(line.c_str(), fp);
+  }
+  for (size_t n = 0; n < s->g.nodes.size(); n++) {     // then nodes (Graph.h:126-130)
+    const HNode& N = s->g.nodes[n];
+    if (!N.alive) continue;
+    std::string line = std::string(N.kind == NODE_POSE ? "Pose3d_Node " : "Plane3d_Node ") + std::to_string(n) + " " +
+                       (N.kind == NODE_POSE ? pose_str(N.v) : plane_str(N.v)) + "\n";
+    std::fputs(line.c_str(), fp);
+  }
+  std::fclose(fp);
+  return 0;
+}
+
+int pus_load_isam_dataset(pus_handle h, const char* path, int* n_poses, int* n_factors) {
+  NEED(h);
+  Solver* s = SV(h);
+  FILE* fp = std::fopen(path, "rb");
+  if (!fp) { g_err = std::string("pus_load_isam_dataset: cannot open ") + path; return -1; }
+  std::map<unsigned, int> mapper;   // dataset pose index -> node id (Loader's _pose_mapper)
+  int added_p = 0, added_f = 0, lineno = 0, rc = 0;
+  char buf[4096];
+  auto node_of = [&](unsigned idx, bool create) {
+    auto it = mapper.find(idx);
+    if (it != mapper.end()) return it->second;
+    if (!create) return -1;
+    const int id = s->g.add_node(NODE_POSE, nullptr);
+    mapper[idx] = id;
+    added_p++;
+    return id;
+  };
+  while (rc == 0 && std::fgets(buf, sizeof buf, fp)) {
+    lineno++;
+    char key[64];
+    int off = 0;
+    if (std::sscanf(buf, "%63s%n", key, &off) != 1) continue;
+    const std::string kw(key);
+    const char* args = buf + off;
+    if (kw == "EDGE3") {   // Loader.cpp:316-365
+      unsigned i0, i1;
+      double x, y, z, roll, pitch, yaw, I[21];
+      int res = std::sscanf(args, "%u %u %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg %lg",
+                            &i0, &i1, &x, &y, &z, &roll, &pitch, &yaw, I, I + 1, I + 2, I + 3, I + 4, I + 5, I + 6, I + 7, I + 8, I + 9, I + 10,
+                            I + 11, I + 12, I + 13, I + 14, I + 15, I + 16, I + 17, I + 18, I + 19, I + 20);
+      if (res != 29 && res != 8) { g_err = "EDGE3: parse error at line " + std::to_string(lineno); rc = -1; break; }
+      double meas[6] = {x, y, z, yaw, pitch, roll};   // Pose3d(x, y, z, yaw, pitch, roll): the file stores roll pitch yaw
+      double si[21];
+      if (res == 8) {
+        int q = 0;
+        for (int r = 0; r < 6; r++) for (int cc = r; cc < 6; cc++) si[q++] = (r == cc) ? 1.0 : 0.0;
+      } else {
+        // rows 0-2 as given; rotational block reversed: [i66 i56 i46; 0 i55 i45; 0 0 i44] (Loader.cpp:343-345)
+        const double i44 = I[15], i45 = I[16], i46 = I[17], i55 = I[18], i56 = I[19], i66 = I[20];
+        const double full[21] = {I[0], I[1], I[2], I[3], I[4], I[5], I[6], I[7], I[8], I[9], I[10], I[11], I[12], I[13], I[14],
+                                 i66, i56, i46, i55, i45, i44};
+        std::memcpy(si, full, sizeof full);
+      }
+      unsigned from, to;
+      if (i0 < i1) { to = i1; from = i0; }
+      else {   // reverse the constraint: delta = Pose3d(delta.oTw())  (Loader.cpp:349-356)
+        double p7[7], Ti[16], inv7[7], yw, pt, rl;
+        pose_from_xyzypr(meas, p7);
+        pose_to_Tinv(p7, Ti);
+        T_to_pose(Ti, inv7);
+        quat_to_euler(inv7 + 3, yw, pt, rl);
+        meas[0] = inv7[0]; meas[1] = inv7[1]; meas[2] = inv7[2]; meas[3] = yw; meas[4] = pt; meas[5] = rl;
+        to = i0; from = i1;
+      }
+      if (mapper.empty()) {   // Loader::add_prior: first pose = dataset index 0, prior at the origin, sqrtinf 100 I
+        const int id0 = node_of(0, true);
+        double zero[6] = {0, 0, 0, 0, 0, 0}, s100[21];
+        int q = 0;
+        for (int r = 0; r < 6; r++) for (int cc = r; cc < 6; cc++) s100[q++] = (r == cc) ? 100.0 : 0.0;
+        if (s->g.add_pose_prior(id0, zero, s100) < 0) { g_err = s->g.err; rc = -1; break; }
+        added_f++;
+      }
+      const int a = node_of(from, false), b = node_of(to, true);
+      if (a < 0) { g_err = "EDGE3: pose " + std::to_string(from) + " not seen before line " + std::to_string(lineno); rc = -1; break; }
+      if (s->g.add_odometry(a, b, meas, si) < 0) { g_err = s->g.err; rc = -1; break; }
+      added_f++;
+    } else if (kw == "POSE3D_INIT") {   // Loader.cpp:366-383
+      unsigned idx;
+      double x, y, z, roll, pitch, yaw;
+      if (std::sscanf(args, "%u %lg %lg %lg %lg %lg %lg", &idx, &x, &y, &z, &roll, &pitch, &yaw) != 7) {
+        g_err = "POSE3D_INIT: parse error at line " + std::to_string(lineno); rc = -1; break;
+      }
+      if (mapper.find(idx) == mapper.end()) {
+        const double v[6] = {x, y, z, yaw, pitch, roll};
+        double p7[7];
+        pose_from_xyzypr(v, p7);
+        const int id = s->g.add_node(NODE_POSE, p7);
+        mapper[idx] = id;
+        added_p++;
+      }
+    } else if (kw == "EDGE3_INIT" || kw == "POSE3D_TRUE" || kw == "EDGE3_TRUE" || kw == "SOLVE") {
+      continue;   // as upstream (Loader.cpp:385-394)
+    } else if (kw[0] == '#') {
+      continue;
+    } else {
+      g_err = "keyword '" + kw + "' (line " + std::to_string(lineno) + ") is not part of the 3-D pose-graph grammar this back end loads";
+      rc = -1;
+    }
+  }
+  std::fclose(fp);
+  if (n_poses) *n_poses = added_p;
+  if (n_factors) *n_factors = added_f;
+  return rc;
+}
+
 long long pus_debug_fetch(pus_handle h, const char* name, double* out, long long cap) {
   NEED(h);
   Solver* s = SV(h);
