@@ -221,6 +221,26 @@ int pus_refresh_plane_measurements(pus_handle h, int n_frames, const int* frame_
  * onto the current device-resident estimate of plane node plane_of_point[i]. */
 int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point, const float* pts_in, float* pts_out);
 
+/* ---- one graph spanning several ranks (second bullet) --------------------------- */
+/* Every rank holds the whole graph (build it identically on each) and runs its own persistent kernel; the PCG
+ * phases -- the two Schur sweeps, the pose phase, the preconditioner, the dot products -- are split over the CTAs of
+ * ALL ranks.  The vectors they exchange (plane partial sums, p, q, r, x, z, the coarse residuals, the reduction
+ * partials) sit in one "mirror arena" per rank; owners store their entries into every peer's arena through
+ * NVLink peer memory and the ranks meet at a cross-rank barrier (system-scope atomics) where the single-GPU path
+ * has its team barrier -- no host round trip and no NCCL call inside the solve.  Linearisation, the Schur
+ * set-up and the LM update are replicated, so all ranks take identical decisions and end with identical estimates.
+ *   pus_span_export   uploads the graph if needed and writes the 64-byte CUDA IPC handle of this rank's arena
+ *   pus_span_connect  opens the peers' handles (handles = world x 64 bytes, in rank order; own entry ignored)
+ *   pus_span_optimize batch_optimization() of the spanning graph; call on every rank
+ *   pus_span_disconnect closes the peer mappings (also done by pus_destroy)
+ * pus_span_emulate_optimize runs the same protocol with `world` handles on ONE device (one CTA team per handle inside
+ * a single launch) -- the test vehicle for the protocol on a single GPU. */
+int pus_span_export(pus_handle h, void* ipc_handle_64);
+int pus_span_connect(pus_handle h, int rank, int world, const void* handles);
+int pus_span_optimize(pus_handle h, int* iterations);
+int pus_span_disconnect(pus_handle h);
+int pus_span_emulate_optimize(pus_handle* handles, int world, int* iterations);
+
 /* ---- graph text I/O (host only) ---------------------------------------------- */
 /* Slam::save (ISAM/isamlib/Slam.cpp:84-89 -> Graph::write, Graph.h:120-131): every factor, then every node, one per
  * line: "<Factor name> <node ids> <measure> {sqrtinf upper triangle, row-wise, comma separated}" (Factor.h:148-155,

@@ -362,6 +362,32 @@ class GpuGraphAPI(GraphAPI):
         self._chk(self.lib.pus_get_stats(self.h, C.byref(s)))
         return s.as_dict()
 
+    def span_export(self):
+        buf = C.create_string_buffer(64)
+        fn = self.lib.pus_span_export
+        fn.argtypes = [C.c_void_p, C.c_void_p]
+        self._chk(fn(self.h, buf))
+        return bytes(buf.raw)
+
+    def span_connect(self, rank, world, handles):
+        blob = b"".join(handles)
+        assert len(blob) == 64 * world
+        fn = self.lib.pus_span_connect
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_char_p]
+        self._chk(fn(self.h, int(rank), int(world), blob))
+
+    def span_optimize(self):
+        it = C.c_int(0)
+        fn = self.lib.pus_span_optimize
+        fn.argtypes = [C.c_void_p, c_int_p]
+        self._chk(fn(self.h, C.byref(it)))
+        return it.value
+
+    def span_disconnect(self):
+        fn = self.lib.pus_span_disconnect
+        fn.argtypes = [C.c_void_p]
+        self._chk(fn(self.h))
+
     def debug_fetch(self, name, cap):
         out = np.zeros(int(cap))
         n = self.lib.pus_debug_fetch(self.h, name.encode(), _dp(out), C.c_longlong(int(cap)))
@@ -391,6 +417,16 @@ def batch_optimize_many(apis):
     if rc < 0:
         raise ApiError((lib.pus_last_error() or b"?").decode())
     return its
+
+
+def span_emulate_optimize(apis):
+    """one graph spanning len(apis) "ranks" emulated on one device (include/popup_gpu.h); every api holds the same graph"""
+    lib = apis[0].lib
+    it = C.c_int(0)
+    rc = lib.pus_span_emulate_optimize(_handles(apis), len(apis), C.byref(it))
+    if rc < 0:
+        raise ApiError((lib.pus_last_error() or b"?").decode())
+    return it.value
 
 
 def upload_many(apis):

@@ -52,7 +52,15 @@ __device__ int schur_setup(Phase& ph, Ctx& c, double lambda, Timer& ft, bool reb
 // Solve (Hpp_d - W Hll_d^-1 W^T) x = -gp + W Hll_d^-1 gl by preconditioned CG, then back-substitute the
 // planes.  Returns |delta|; *its = PCG iterations.
 // `warm`: start from the previous solution (kept in G.xprev) -- used after a rejected LM step, where only lambda changed.
+__device__ __forceinline__ void span_view(Ctx& c, bool global) {
+  if (c.span_w <= 1) return;
+  if (global) { c.rank = c.span_r * c.ltsize + c.lrank; c.tsize = c.span_w * c.ltsize; c.mirror = 1; }
+  else { c.rank = c.lrank; c.tsize = c.ltsize; c.mirror = 0; }
+}
+
 __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambda, int acinv, int* its, Timer& ft, bool warm) {
+  // spanning solve: the PCG phases are split over the CTAs of all ranks (every rank keeps full copies of the vectors)
+  span_view(c, true);
   if (!c.use_tma) {   // (large graphs use that shared memory for the TMA staging buffers instead)
     ph.cache_blocks();
     c.smem_cache_ok = 1;
@@ -118,10 +126,11 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
   team_barrier(c);
   v[0] = ph.solve_planes(1) + ph.norm_x();  // (also keeps a copy of x for the next warm start)
   team_reduce<1>(c, G.red, v);
+  span_view(c, false);
   return sqrt(v[0]);
 }
 
-__device__ void run_graph(const DevGraph& G, Ctx& c) {
+__device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
   Phase ph(G, c);
   const LmParams& P = G.prm;
   const bool lead = (c.rank == 0 && threadIdx.x == 0);
@@ -134,6 +143,11 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
     res->trace_n = 0; res->status = 0; res->chi2_initial = 0; res->chi2_final = 0;
     for (int i = 0; i < 24; i++) res->phase_ns[i] = 0;
   }
+  c.span_w = G.span_w > 1 ? G.span_w : 1;
+  c.span_r = G.span_r;
+  c.lrank = c.rank; c.ltsize = c.tsize; c.mirror = 0;
+  for (int w = 0; w < 8; w++) c.peer_delta[w] = G.peer_delta[w];
+  c.gbar = G.gbar;
   c.use_tma = (P.tma_mode == 1) || (P.tma_mode == 0 && G.ntile_pl > 2 * c.tsize * kWarps);
   c.smem_cache_ok = 0;
   if (P.restore_init) { ph.restore_init(); team_barrier(c); }
@@ -297,6 +311,17 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
   }
 }
 
+// spanning solves keep the cross-rank barrier count across launches (every rank executes the same number of global
+// barriers per solve, so the counters are never reset while peers may already be running)
+__device__ void run_graph(const DevGraph& G, Ctx& c) {
+  if (G.span_w > 1 && threadIdx.x == 0) c.gbar_target = __ldcg(G.gbar + 1);
+  run_graph_impl(G, c);
+  if (G.span_w > 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) G.gbar[1] = c.gbar_target;
+  }
+}
+
 __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs, int n_graphs, int team_ctas, unsigned* bars) {
   extern __shared__ __align__(128) unsigned char smem[];
   __shared__ DevGraph sG;
@@ -314,6 +339,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
   c.use_tma = 0;
   c.tma_par = 0;
   c.gj_par = 0;
+  c.span_w = 1; c.span_r = 0; c.mirror = 0; c.gbar = nullptr; c.gbar_target = 0;
   if (threadIdx.x == 0) {
     unsigned long long* gbar = reinterpret_cast<unsigned long long*>(smem + kSmGjBar);
     mbar_init(gbar, 1);
@@ -360,6 +386,11 @@ struct Solver {
   Compiled c;
   uint64_t compiled_topo = 0;
   bool meas_dirty = true;
+  int span_w = 1, span_r = 0;  // one graph spanning ranks: world / rank and the peers' arenas (CUDA IPC mappings)
+  std::vector<void*> span_peers;
+  uint64_t span_topo = 0;
+  double* arena = nullptr;     // mirror arena of the last upload (DevGraph::gbar + the PCG vectors)
+  size_t arena_bytes = 0;
   void* scratch = nullptr;     // grow-only device scratch of the refresh / projection entry points
   size_t scratch_bytes = 0;
   std::vector<int> fid2slot;   // pose-plane factor id -> pose-major edge slot (built on demand)
@@ -503,14 +534,35 @@ static int upload(Solver* s) {
     AL(W, T * kWStride, "Wtiles"); AL(Wt, TL * kWStride, "Wttiles"); AL(JP, E * 21, "JP"); AL(JL, E * 12, "JL");
     AL(PF, (size_t)c.Epf * 120, "PF"); AL(LP, (size_t)c.Elp * 12, "LP");
     AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
-    AL(vl, M * 3, "vl"); AL(dl, M * 3, "dl"); AL(upart, (size_t)c.n_upart * 3, "upart"); AL(ypart, 8, "ypart");
+    AL(ypart, 8, "ypart");
     AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc"); AL(Yc, (size_t)c.nce * 18, "Yc");
     AL(Ac[0], ac_doubles(6 * c.nc_pad), "Ac0"); AL(Ac[1], ac_doubles(6 * c.nc_pad), "Ac1");
-    AL(x, N * 6, "x"); AL(r, N * 6, "r"); AL(z, N * 6, "z"); AL(q, N * 6, "q"); AL(b, N * 6, "b");
-    AL(pv[0], N * 6, "pv0"); AL(pv[1], N * 6, "pv1"); AL(xprev, N * 6, "xprev"); AL(zc, (size_t)6 * c.nc, "zc");
-    AL(rcpart[0], (size_t)c.nblk * 12, "rcpart0"); AL(rcpart[1], (size_t)c.nblk * 12, "rcpart1"); AL(qcpart, (size_t)c.nblk * 12, "qcpart");
-    AL(red, (size_t)4 * 4 * 1024, "red");
 #undef AL
+    {
+      // The vectors the PCG phases exchange live in ONE allocation (the "mirror arena"): when one graph spans several
+      // ranks every rank lays it out identically, so a peer's copy of any element is at a fixed byte offset.
+      struct Item { double** p; size_t n; const char* name; };
+      const Item items[] = {
+          {&d.vl, M * 3, "vl"}, {&d.dl, M * 3, "dl"}, {&d.upart, (size_t)c.n_upart * 3, "upart"},
+          {&d.x, N * 6, "x"}, {&d.r, N * 6, "r"}, {&d.z, N * 6, "z"}, {&d.q, N * 6, "q"}, {&d.b, N * 6, "b"},
+          {&d.pv[0], N * 6, "pv0"}, {&d.pv[1], N * 6, "pv1"}, {&d.xprev, N * 6, "xprev"}, {&d.zc, (size_t)6 * c.nc, "zc"},
+          {&d.rcpart[0], (size_t)c.nblk * 12, "rcpart0"}, {&d.rcpart[1], (size_t)c.nblk * 12, "rcpart1"},
+          {&d.qcpart, (size_t)c.nblk * 12, "qcpart"}, {&d.red, (size_t)4 * 4 * 2048, "red"}};
+      size_t total = 32;   // first 256 bytes: the cross-rank barrier counter and its persisted target
+      for (const Item& it : items) total += (std::max<size_t>(it.n, 1) + 31) / 32 * 32;
+      double* arena = nullptr;
+      if (s->dalloc(&arena, total) < 0) return -1;
+      CUDA_OK(cudaMemsetAsync(arena, 0, 256, s->stream));
+      s->arena = arena; s->arena_bytes = total * sizeof(double);
+      d.gbar = reinterpret_cast<unsigned*>(arena);
+      size_t off = 32;
+      for (const Item& it : items) {
+        *it.p = arena + off;
+        s->named[it.name] = std::make_pair(arena + off, it.n);
+        off += (std::max<size_t>(it.n, 1) + 31) / 32 * 32;
+      }
+      d.span_w = 1; d.span_r = 0;
+    }
     CUDA_OK(cudaMemsetAsync(d.W, 0, T * kWStride * sizeof(double), s->stream));
     CUDA_OK(cudaMemsetAsync(d.Wt, 0, TL * kWStride * sizeof(double), s->stream));
     if (s->dalloc(&s->d_graph, 1) < 0 || s->dalloc(&s->d_res, 1) < 0 || s->dalloc(&s->d_trace, 1) < 0 ||
@@ -750,6 +802,7 @@ int pus_destroy(pus_handle h) {
   NEED(h);
   Solver* s = SV(h);
   cudaSetDevice(s->device);
+  for (void* pp : s->span_peers) if (pp) cudaIpcCloseMemHandle(pp);
   s->free_device();
   if (s->scratch) cudaFree(s->scratch);
   if (s->ev0) cudaEventDestroy(s->ev0);
@@ -957,6 +1010,81 @@ int pus_batch_optimize_many(pus_handle* hs, int n, int* iters) {
   if (solve_many(hs, n, iters, MODE_BATCH, 0) < 0) return -1;
   return pus_download_many(hs, n);
 }
+// ---- one graph spanning several ranks ----
+int pus_span_export(pus_handle h, void* out64) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (upload(s) < 0) return -1;
+  cudaIpcMemHandle_t mh;
+  CUDA_OK(cudaIpcGetMemHandle(&mh, s->arena));
+  static_assert(sizeof(mh) == 64, "CUDA IPC handle size");
+  std::memcpy(out64, &mh, 64);
+  return 0;
+}
+int pus_span_disconnect(pus_handle h) {
+  NEED(h);
+  Solver* s = SV(h);
+  for (void* p : s->span_peers) if (p) cudaIpcCloseMemHandle(p);
+  s->span_peers.clear();
+  s->span_w = 1; s->span_r = 0;
+  return 0;
+}
+int pus_span_connect(pus_handle h, int rank, int world, const void* handles) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (world < 1 || world > 8 || rank < 0 || rank >= world) { g_err = "pus_span_connect: world must be 1..8"; return -1; }
+  if (!s->uploaded || !s->arena) { g_err = "pus_span_connect: call pus_span_export first"; return -1; }
+  pus_span_disconnect(h);
+  CUDA_OK(cudaSetDevice(s->device));
+  s->span_peers.assign(world, nullptr);
+  for (int w = 0; w < world; w++) {
+    if (w == rank) continue;
+    cudaIpcMemHandle_t mh;
+    std::memcpy(&mh, static_cast<const char*>(handles) + 64 * (size_t)w, 64);
+    void* p = nullptr;
+    cudaError_t e = cudaIpcOpenMemHandle(&p, mh, cudaIpcMemLazyEnablePeerAccess);
+    if (e != cudaSuccess) { g_err = std::string("cudaIpcOpenMemHandle (peer ") + std::to_string(w) + "): " + cudaGetErrorString(e); pus_span_disconnect(h); return -1; }
+    s->span_peers[w] = p;
+  }
+  s->span_w = world; s->span_r = rank;
+  s->span_topo = s->compiled_topo;
+  return 0;
+}
+static void span_fill(Solver* s, int rank, int world, const std::vector<char*>& arenas) {
+  s->hd.span_w = world; s->hd.span_r = rank;
+  for (int w = 0; w < 8; w++) s->hd.peer_delta[w] = (w < world) ? (long long)(arenas[w] - arenas[rank]) : 0;
+}
+int pus_span_optimize(pus_handle h, int* iters) {
+  NEED(h);
+  Solver* s = SV(h);
+  if (s->span_w <= 1) { g_err = "pus_span_optimize: not connected"; return -1; }
+  if (upload(s) < 0) return -1;   // values only: a rebuild would move the arena the peers have mapped
+  if (s->span_topo != s->compiled_topo) { g_err = "pus_span_optimize: the graph changed since pus_span_connect; export / connect again"; return -1; }
+  std::vector<char*> arenas(s->span_w);
+  for (int w = 0; w < s->span_w; w++) arenas[w] = (w == s->span_r) ? reinterpret_cast<char*>(s->arena) : static_cast<char*>(s->span_peers[w]);
+  span_fill(s, s->span_r, s->span_w, arenas);
+  int rc = solve_many(&h, 1, iters, MODE_BATCH, 0);
+  s->hd.span_w = 1; s->hd.span_r = 0;
+  if (rc < 0) return -1;
+  return download(&s, 1);
+}
+int pus_span_emulate_optimize(pus_handle* hs, int world, int* iters) {
+  if (world < 1 || world > 8) { g_err = "pus_span_emulate_optimize: world must be 1..8"; return -1; }
+  Solver* s0 = SV(hs[0]);
+  if (ensure_device(s0) < 0) return -1;
+  for (int i = 1; i < world; i++) adopt_stream(SV(hs[i]), s0->stream);
+  if (pus_upload_many(hs, world) < 0) return -1;
+  std::vector<char*> arenas(world);
+  for (int i = 0; i < world; i++) arenas[i] = reinterpret_cast<char*>(SV(hs[i])->arena);
+  for (int i = 0; i < world; i++) span_fill(SV(hs[i]), i, world, arenas);
+  std::vector<int> its(world, 0);
+  int rc = solve_many(hs, world, its.data(), MODE_BATCH, 0);
+  for (int i = 0; i < world; i++) { SV(hs[i])->hd.span_w = 1; SV(hs[i])->hd.span_r = 0; }
+  if (rc < 0) return -1;
+  if (iters) *iters = its[0];
+  return pus_download_many(hs, world);
+}
+
 // Slam::update (Slam.cpp:157-196). PPS runs with mod_batch = 1 => every call is the batch step
 // (relinearise + one Gauss-Newton step). Other settings would need iSAM's Givens incremental path.
 int pus_update(pus_handle h) {

@@ -89,6 +89,11 @@ struct DevGraph {
   double *x, *r, *z, *q, *b, *pv[2], *xprev, *zc;
   double *rcpart[2], *qcpart;
   double *red;
+  // one graph spanning several ranks: rank / world, byte offsets from this rank's mirrored arena
+  // to every peer's (0 for itself), and the cross-rank barrier counter that lives inside the arena
+  int span_w, span_r;
+  long long peer_delta[8];
+  unsigned* gbar;
   LmParams prm;
   LmResult* res;
   LmTrace* trace;
@@ -104,6 +109,13 @@ struct Ctx {
   int use_tma;           // this graph streams its W / Wt tiles through the per-warp TMA staging buffers
   unsigned tma_par;      // phase parity of this warp's two staging mbarriers (bit s = stage s)
   unsigned gj_par;       // phase parity of the coarse inversion's two panel mbarriers
+  // spanning mode: the team seen by the split PCG phases covers the CTAs of all ranks (rank = span_r * ltsize + lrank);
+  // the replicated phases (linearise, Schur set-up, update) use the local view.  `mirror` = stores to the shared PCG
+  // vectors are repeated into every peer's arena.
+  int span_w, span_r, lrank, ltsize, mirror;
+  long long peer_delta[8];
+  unsigned* gbar;
+  unsigned gbar_target;  // thread 0 only
   unsigned char* smem;   // dynamic shared memory
 };
 
@@ -122,9 +134,32 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
   return v;
 }
 
-// All CTAs of the team must call this the same number of times.
+__device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// All CTAs of the team must call this the same number of times.  In the global view of a spanning solve the barrier
+// covers the CTAs of every rank: each CTA adds one to its own rank's counter and to every peer's (system-scope
+// atomics through peer-mapped memory), and waits for its own counter.
 __device__ __forceinline__ void team_barrier(Ctx& c) {
   __syncthreads();
+  if (c.mirror) {
+    if (threadIdx.x == 0) {
+      c.gbar_target += (unsigned)c.tsize;
+      __threadfence_system();
+      for (int w = 0; w < c.span_w; w++)
+        atomicAdd_system(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(c.gbar) + c.peer_delta[w]), 1u);
+      const unsigned long long t0 = gtime();
+      while (ld_acquire_sys_u32(c.gbar) < c.gbar_target) {
+        if (gtime() - t0 > 20000000000ull) __trap();   // a peer never arrived (20 s): fail instead of hanging the GPU
+      }
+      __threadfence_system();
+    }
+    __syncthreads();
+    return;
+  }
   if (c.tsize > 1) {
     if (threadIdx.x == 0) {
       c.bar_target += (unsigned)c.tsize;
@@ -135,6 +170,15 @@ __device__ __forceinline__ void team_barrier(Ctx& c) {
     }
     __syncthreads();
   }
+}
+
+// store to a PCG vector that every rank keeps a full copy of (no-op distinction outside the spanning global view)
+template <typename T>
+__device__ __forceinline__ void put(const Ctx& c, T* p, T v) {
+  *p = v;
+  if (c.mirror)
+    for (int w = 0; w < c.span_w; w++)
+      if (w != c.span_r) *reinterpret_cast<T*>(reinterpret_cast<char*>(p) + c.peer_delta[w]) = v;
 }
 
 __device__ __forceinline__ double warp_sum(double v) {
@@ -273,7 +317,7 @@ __device__ __forceinline__ void team_reduce(Ctx& c, double* red, double* v) {
       double acc = (lane < kWarps) ? s[lane * 4 + k] : 0.0;
       acc = warp_sum(acc);
       if (lane == 0) {
-        if (c.tsize > 1) red[((size_t)c.red_slot * c.tsize + c.rank) * 4 + k] = acc;
+        if (c.tsize > 1) put(c, &red[((size_t)c.red_slot * c.tsize + c.rank) * 4 + k], acc);
         else s[kWarps * 4 + k] = acc;
       }
     }
@@ -1142,7 +1186,7 @@ struct Phase {
         const int pk = __shfl_up_sync(0xffffffffu, keyC, 1);
         if (keyC >= 0 && (lane == 0 || pk != keyC)) {
           double* o = G.upart + (size_t)G.pl_part[tile * 32 + lane] * 3;
-          o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+          put(c, o, u[0]); put(c, o + 1, u[1]); put(c, o + 2, u[2]);
         }
 #pragma unroll
         for (int a = 0; a < 6; a++) x[a] = xn[a];
@@ -1177,7 +1221,7 @@ struct Phase {
       int pk = __shfl_up_sync(0xffffffffu, key, 1);
       if (key >= 0 && (lane == 0 || pk != key)) {
         double* o = G.upart + (size_t)G.pl_part[s] * 3;
-        o[0] = u[0]; o[1] = u[1]; o[2] = u[2];
+        put(c, o, u[0]); put(c, o + 1, u[1]); put(c, o + 2, u[2]);
       }
     }
   }
@@ -1198,7 +1242,7 @@ struct Phase {
         double* o = (mode == 0 ? G.vl : G.dl) + (size_t)l * 3;
         for (int t = 0; t < 3; t++) {
           double v = Hi[t * 3] * u[0] + Hi[t * 3 + 1] * u[1] + Hi[t * 3 + 2] * u[2];
-          o[t] = v;
+          put(c, o + t, v);
           nrm += v * v;
         }
       }
@@ -1236,8 +1280,8 @@ struct Phase {
         for (int w = 0; w < kWarps; w++)
           for (int b = 0; b < 3; b++) tot[b] += s[w * 4 + b];
         const int o = threadIdx.x;
-        G.vl[(size_t)l * 3 + o] = ldc(G.Hinv + (size_t)l * 9 + o * 3) * tot[0] + ldc(G.Hinv + (size_t)l * 9 + o * 3 + 1) * tot[1] +
-                                  ldc(G.Hinv + (size_t)l * 9 + o * 3 + 2) * tot[2];
+        put(c, &G.vl[(size_t)l * 3 + o], ldc(G.Hinv + (size_t)l * 9 + o * 3) * tot[0] + ldc(G.Hinv + (size_t)l * 9 + o * 3 + 1) * tot[1] +
+                                             ldc(G.Hinv + (size_t)l * 9 + o * 3 + 2) * tot[2]);
       }
       __syncthreads();
     }
@@ -1259,8 +1303,8 @@ struct Phase {
       }
       for (int b = 0; b < 3; b++) uu[b] = warp_sum(uu[b]);
       if (lane < 3)
-        G.vl[(size_t)l * 3 + lane] = ldc(G.Hinv + (size_t)l * 9 + lane * 3) * uu[0] + ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 1) * uu[1] +
-                                     ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 2) * uu[2];
+        put(c, &G.vl[(size_t)l * 3 + lane], ldc(G.Hinv + (size_t)l * 9 + lane * 3) * uu[0] + ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 1) * uu[1] +
+                                                ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 2) * uu[2]);
     }
   }
 
@@ -1274,7 +1318,7 @@ struct Phase {
       int p0 = k * kBlockPoses, c0 = p0 / G.SP;
       double acc = 0;
       for (int pi = 0; pi < np; pi++) acc += hat(p0 + pi, c0 + node) * sv[slot * kBlockDim + pi * 6 + row];
-      out[(size_t)k * 12 + u] = acc;
+      put(c, &out[(size_t)k * 12 + u], acc);
     }
   }
 
@@ -1288,8 +1332,8 @@ struct Phase {
         const int row = u % 6;
         size_t o = (size_t)p * 6 + row;
         const int c0 = p / G.SP;
-        G.pv[cur ^ 1][o] = ldc(G.z + o) + beta * ldc(G.pv[cur] + o) + hat(p, c0) * ldc(G.zc + (size_t)c0 * 6 + row) +
-                           hat(p, c0 + 1) * ldc(G.zc + (size_t)min(c0 + 1, G.nc - 1) * 6 + row);
+        put(c, &G.pv[cur ^ 1][o], ldc(G.z + o) + beta * ldc(G.pv[cur] + o) + hat(p, c0) * ldc(G.zc + (size_t)c0 * 6 + row) +
+                           hat(p, c0 + 1) * ldc(G.zc + (size_t)min(c0 + 1, G.nc - 1) * 6 + row));
       }
     }
   }
@@ -1453,7 +1497,8 @@ struct Phase {
         const size_t o = (size_t)p * 6 + row;
         if (rhs) {
           double v = -ldc(G.gp + o) + ysum;
-          G.b[o] = v; G.r[o] = v; G.x[o] = 0.0; G.pv[0][o] = 0.0; G.pv[1][o] = 0.0; G.z[o] = 0.0; G.q[o] = 0.0;
+          put(c, &G.b[o], v); put(c, &G.r[o], v); put(c, &G.x[o], 0.0); put(c, &G.pv[0][o], 0.0); put(c, &G.pv[1][o], 0.0);
+          put(c, &G.z[o], 0.0); put(c, &G.q[o], 0.0);
           sA[slot * kBlockDim + u] = v;
         } else {
           const double* H = G.Hpp + (size_t)p * 36 + row * 6;
@@ -1501,7 +1546,7 @@ struct Phase {
             }
           }
           v -= ysum;
-          qout[o] = v;
+          put(c, &qout[o], v);
           sA[slot * kBlockDim + u] = v;
           dot += pr * v;
         }
@@ -1625,7 +1670,7 @@ struct Phase {
         }
         for (; j < ldm; j += 32) acc += ldc(arow + (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk)) * src[j];
         acc = warp_sum(acc);
-        if (lane == 0) { G.zc[i] = acc; dot += src[i] * acc; }
+        if (lane == 0) { put(c, &G.zc[i], acc); dot += src[i] * acc; }
       }
     }
     lap(14);
@@ -1658,8 +1703,8 @@ struct Phase {
           if (on && !first) {
             const size_t o = (size_t)p * 6 + u % 6;
             rn -= alpha * vq[t];
-            G.x[o] = vx[t] + alpha * vp[t];
-            G.r[o] = rn;
+            put(c, &G.x[o], vx[t] + alpha * vp[t]);
+            put(c, &G.r[o], rn);
           }
           sR[(rd * kSlots + slot) * kBlockDim + u] = on ? rn : 0.0;
         }
@@ -1687,7 +1732,7 @@ struct Phase {
           for (int j = 0; j < kBlockDim; j++) zl += B[j * kBlockDim] * rv[j];
           const int p = k * kBlockPoses + tid / 6;
           if (p < G.N) {
-            G.z[(size_t)p * 6 + tid % 6] = zl;
+            put(c, &G.z[(size_t)p * 6 + tid % 6], zl);
             dot += rv[tid] * zl;
           }
         } else if (tid >= 128 && tid < 128 + 12) {
@@ -1713,8 +1758,8 @@ struct Phase {
         if (!first) {
           double pp = ldc(pvec + o), qq = ldc(G.q + o), xx = ldc(G.x + o);
           rn -= alpha * qq;
-          G.x[o] = xx + alpha * pp;
-          G.r[o] = rn;
+          put(c, &G.x[o], xx + alpha * pp);
+          put(c, &G.r[o], rn);
         }
         sA[slot * kBlockDim + u] = rn;
       }
@@ -1736,7 +1781,7 @@ struct Phase {
 #pragma unroll 32
           for (int j = 0; j < kBlockDim; j++) zl += ldc(B + (size_t)j * kBlockDim) * sA[slot * kBlockDim + j];
         }
-        G.z[(size_t)p * 6 + row] = zl;
+        put(c, &G.z[(size_t)p * 6 + row], zl);
         dot += rn * zl;
       }
     }
@@ -1747,7 +1792,7 @@ struct Phase {
   // -------- |x|^2 over owned poses --------
   __device__ double norm_x() {
     double acc = 0;
-    for (int i = tid_team(); i < G.N * 6; i += nthr_team()) { double v = ldc(G.x + i); acc += v * v; G.xprev[i] = v; }
+    for (int i = tid_team(); i < G.N * 6; i += nthr_team()) { double v = ldc(G.x + i); acc += v * v; put(c, &G.xprev[i], v); }
     return acc;
   }
 

@@ -2,9 +2,10 @@
 round-robined over ranks, one process per GPU, no data-path collective.  torch.distributed is
 only used to gather the solved estimates / reduce the timing (NCCL on GPUs, gloo in the CPU test-suite).
 
-A single graph spanning several ranks would need one all-reduce per PCG iteration (the two dot products plus the
-partial plane sums of the planes shared across the cut); that split is not implemented in this round -- see
-DESIGN.md "Multi-GPU".
+One graph spanning several ranks (`span_optimize`): every rank builds the same graph; the PCG phases are split
+over the CTAs of all ranks inside the persistent kernels, which exchange their vectors through CUDA-IPC-mapped peer
+memory and meet at a cross-rank barrier -- torch.distributed only carries the 64-byte IPC handles (DESIGN.md
+"Multi-GPU").
 """
 import numpy as np
 
@@ -63,3 +64,23 @@ def reduce_throughput(units, seconds, world=1, device=None):
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dist.all_reduce(u, op=dist.ReduceOp.SUM)
     return float(u.item()), float(t.item())
+
+
+def span_optimize(api, rank=0, world=1):
+    """batch_optimization() of ONE graph held identically by every rank (GpuGraphAPI `api` on this rank's GPU).
+    Exchanges the arenas' CUDA IPC handles over torch.distributed, connects, solves; returns the LM iteration count.
+    All ranks end with the same estimates."""
+    if world == 1:
+        return api.batch_optimize()
+    import torch.distributed as dist
+    mine = api.span_export()
+    handles = [None] * world
+    dist.all_gather_object(handles, mine)
+    api.span_connect(rank, world, handles)
+    dist.barrier()
+    try:
+        it = api.span_optimize()
+    finally:
+        dist.barrier()
+        api.span_disconnect()
+    return it

@@ -152,6 +152,38 @@ def test_large_graph_streaming_path():
     assert gpu.stats()["grid_ctas"] >= 120
 
 
+@pytest.mark.parametrize("cfg,world,kw", [(2, 2, {}), (2, 3, {}), (3, 2, dict(n_poses=600, n_planes=60, max_iterations=8))])
+def test_one_graph_spanning_ranks_emulated(cfg, world, kw):
+    """SURVEY 8e, second bullet: one graph split over several ranks.  The protocol (global ownership of tiles / blocks
+    / coarse rows, mirrored stores into every rank's arena, cross-rank barrier, replicated LM driver) run with `world`
+    CTA teams on one device; same LM trace as the single-team solve and as the oracle, all "ranks" end identical."""
+    g = gg.make_config(cfg, seed=1, **kw)
+    one = GpuGraphAPI()
+    i1 = gg.build_bulk(one, g)
+    gg.configure(one, g)
+    it1 = one.batch_optimize()
+    orc = OracleAPI()
+    orc.set_jacobian_mode(1)
+    io = gg.build_bulk(orc, g)
+    gg.configure(orc, g)
+    orc.batch_optimize()
+    apis, infos = [], []
+    for _ in range(world):
+        a = GpuGraphAPI()
+        infos.append(gg.build_bulk(a, g))
+        gg.configure(a, g)
+        apis.append(a)
+    its = capi.span_emulate_optimize(apis)
+    assert its == it1
+    P1 = one.get_poses(i1["pose_ids"])
+    for a, info in zip(apis, infos):
+        assert np.array_equal(a.trace()["accepted"], one.trace()["accepted"])
+        assert np.allclose(a.trace()["chi2_new"], one.trace()["chi2_new"], rtol=1e-9)
+        assert np.abs(a.get_poses(info["pose_ids"]) - P1).max() <= 1e-8
+        compare(a, orc, info, io)
+    assert np.array_equal(apis[0].get_poses(infos[0]["pose_ids"]), apis[-1].get_poses(infos[-1]["pose_ids"]))   # bit-identical ranks
+
+
 def test_gauss_newton_and_update_match_oracle():
     g = gg.make_config(2, seed=1)
     for which in ("gn", "update"):
