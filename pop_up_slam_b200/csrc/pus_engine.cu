@@ -122,6 +122,7 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
   }
   *its = it;
   // planes: dl = Hll_d^-1 (-gl - W^T x)
+  if (c.mirror) { ph.publish_x(); team_barrier(c); }
   ph.sweep_planes(G.x, nullptr, 0.0);
   team_barrier(c);
   v[0] = ph.solve_planes(1) + ph.norm_x();  // (also keeps a copy of x for the next warm start)

@@ -1546,7 +1546,7 @@ struct Phase {
             }
           }
           v -= ysum;
-          put(c, &qout[o], v);
+          qout[o] = v;   // (q is only read back by the owner of the block: not mirrored)
           sA[slot * kBlockDim + u] = v;
           dot += pr * v;
         }
@@ -1703,8 +1703,8 @@ struct Phase {
           if (on && !first) {
             const size_t o = (size_t)p * 6 + u % 6;
             rn -= alpha * vq[t];
-            put(c, &G.x[o], vx[t] + alpha * vp[t]);
-            put(c, &G.r[o], rn);
+            G.x[o] = vx[t] + alpha * vp[t];   // x, r: owner-only during the iteration (x is published once at the end)
+            G.r[o] = rn;
           }
           sR[(rd * kSlots + slot) * kBlockDim + u] = on ? rn : 0.0;
         }
@@ -1732,7 +1732,7 @@ struct Phase {
           for (int j = 0; j < kBlockDim; j++) zl += B[j * kBlockDim] * rv[j];
           const int p = k * kBlockPoses + tid / 6;
           if (p < G.N) {
-            put(c, &G.z[(size_t)p * 6 + tid % 6], zl);
+            G.z[(size_t)p * 6 + tid % 6] = zl;   // large graphs: only the owner reads z (update_direction)
             dot += rv[tid] * zl;
           }
         } else if (tid >= 128 && tid < 128 + 12) {
@@ -1758,8 +1758,8 @@ struct Phase {
         if (!first) {
           double pp = ldc(pvec + o), qq = ldc(G.q + o), xx = ldc(G.x + o);
           rn -= alpha * qq;
-          put(c, &G.x[o], xx + alpha * pp);
-          put(c, &G.r[o], rn);
+          G.x[o] = xx + alpha * pp;
+          G.r[o] = rn;
         }
         sA[slot * kBlockDim + u] = rn;
       }
@@ -1787,6 +1787,19 @@ struct Phase {
     }
     lap(15);
     return dot;
+  }
+
+  // -------- spanning solves: the owners publish the final x to every rank (during the iteration x is owner-only) ----
+  __device__ void publish_x() {
+    if (!c.mirror) return;
+    const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
+    for (int rd = 0; rd < rounds(); rd++) {
+      const int k = c.rank + c.tsize * (slot + kSlots * rd), p = k * kBlockPoses + u / 6;
+      if (slot < kSlots && k < G.nblk && p < G.N) {
+        const size_t o = (size_t)p * 6 + u % 6;
+        put(c, &G.x[o], ldc(G.x + o));
+      }
+    }
   }
 
   // -------- |x|^2 over owned poses --------

@@ -152,15 +152,27 @@ def test_large_graph_streaming_path():
     assert gpu.stats()["grid_ctas"] >= 120
 
 
-@pytest.mark.parametrize("cfg,world,kw", [(2, 2, {}), (2, 3, {}), (3, 2, dict(n_poses=600, n_planes=60, max_iterations=8))])
+@pytest.mark.parametrize("cfg,world,kw", [(2, 2, {}), (2, 3, {}), (3, 2, dict(n_poses=600, n_planes=60, max_iterations=8)),
+                                          (3, 2, dict(n_poses=700, n_planes=70, max_iterations=6, force_large_path=True))])
 def test_one_graph_spanning_ranks_emulated(cfg, world, kw):
     """SURVEY 8e, second bullet: one graph split over several ranks.  The protocol (global ownership of tiles / blocks
     / coarse rows, mirrored stores into every rank's arena, cross-rank barrier, replicated LM driver) run with `world`
     CTA teams on one device; same LM trace as the single-team solve and as the oracle, all "ranks" end identical."""
+    import ctypes
+    kw = dict(kw)
+    large = kw.pop("force_large_path", False)   # the large-graph data path (bulk-copy staging, published direction, heavy planes)
+
+    def options(api):
+        if large:
+            o = api.get_solver_options()
+            o.reserved[2] = 2
+            api._chk(api.lib.pus_set_solver_options(api.h, ctypes.byref(o)))
+
     g = gg.make_config(cfg, seed=1, **kw)
     one = GpuGraphAPI()
     i1 = gg.build_bulk(one, g)
     gg.configure(one, g)
+    options(one)
     it1 = one.batch_optimize()
     orc = OracleAPI()
     orc.set_jacobian_mode(1)
@@ -172,6 +184,7 @@ def test_one_graph_spanning_ranks_emulated(cfg, world, kw):
         a = GpuGraphAPI()
         infos.append(gg.build_bulk(a, g))
         gg.configure(a, g)
+        options(a)
         apis.append(a)
     its = capi.span_emulate_optimize(apis)
     assert its == it1

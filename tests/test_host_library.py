@@ -142,6 +142,12 @@ def test_no_cpu_fallback_without_a_gpu():
         a.refresh_plane_measurements(ids["pose_ids"][:1], [0, 1], np.zeros((1, 4), np.float32), np.eye(3), ids["pp_fids"][:1], [0], [0])
     with pytest.raises(capi.ApiError, match="no CUDA device|CUDA"):
         a.project_to_planes(ids["plane_ids"][:1], np.zeros((1, 3), np.float32))
+    with pytest.raises(capi.ApiError, match="no CUDA device|CUDA"):
+        a.span_export()
+    with pytest.raises(capi.ApiError, match="pus_span_export first"):
+        a.span_connect(0, 2, [b"\0" * 64, b"\0" * 64])
+    with pytest.raises(capi.ApiError, match="not connected"):
+        a.span_optimize()
 
 
 def test_isam_dataset_loader_and_graph_save(tmp_path):
