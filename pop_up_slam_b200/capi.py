@@ -71,9 +71,10 @@ class ApiError(RuntimeError):
     pass
 
 
-def load_library(path=LIB_PATH):
+def load_library(path=None):
     """Load libpopup_gpu.so. Fails loudly when the CUDA library has not been built -- there is no
     CPU fallback behind this ABI."""
+    path = path or os.environ.get("PUS_LIBRARY", LIB_PATH)   # (PUS_LIBRARY: A/B builds of the same ABI)
     if not os.path.exists(path):
         raise ApiError(f"{path} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(nvcc, sm_100a). There is no CPU fallback.")

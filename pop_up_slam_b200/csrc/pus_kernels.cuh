@@ -12,12 +12,10 @@
 //   update      exmap of every vertex, trial chi2, accept / reject, lambda rule -- all on device
 // Control flow follows Optimizer::levenberg_marquardt / gauss_newton / relinearize of the reference
 // (pop_planar_slam/Thirdparty/isam/isamlib/Optimizer.cpp:371-467, 286-366, 114-185).
-#pragma once
-#include <cuda_runtime.h>
-
-#include "pus_graph.hpp"
-
-namespace pus {
+//
+// This file is included TWICE by pus_engine.cu, inside namespace pus::kplain (PUS_NO_SPAN defined: the single-GPU
+// kernel, stores and barriers compiled without the spanning hooks) and inside pus::kspan (one graph spanning
+// ranks).  It therefore has no include guard, no #include and no namespace of its own.
 
 constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
@@ -145,6 +143,7 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
 // atomics through peer-mapped memory), and waits for its own counter.
 __device__ __forceinline__ void team_barrier(Ctx& c) {
   __syncthreads();
+#ifndef PUS_NO_SPAN
   if (c.mirror) {
     if (threadIdx.x == 0) {
       c.gbar_target += (unsigned)c.tsize;
@@ -160,6 +159,7 @@ __device__ __forceinline__ void team_barrier(Ctx& c) {
     __syncthreads();
     return;
   }
+#endif
   if (c.tsize > 1) {
     if (threadIdx.x == 0) {
       c.bar_target += (unsigned)c.tsize;
@@ -176,6 +176,9 @@ __device__ __forceinline__ void team_barrier(Ctx& c) {
 template <typename T>
 __device__ __forceinline__ void put(const Ctx& c, T* p, T v) {
   *p = v;
+#ifdef PUS_NO_SPAN
+  return;
+#endif
   if (c.mirror)
     for (int w = 0; w < c.span_w; w++)
       if (w != c.span_r) *reinterpret_cast<T*>(reinterpret_cast<char*>(p) + c.peer_delta[w]) = v;
@@ -1831,5 +1834,3 @@ struct Phase {
     for (int i = tid_team(); i < G.M * 4; i += nthr_team()) G.plane_lin[i] = ldc(G.plane_trial + i);
   }
 };
-
-}  // namespace pus
