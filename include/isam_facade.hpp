@@ -398,6 +398,30 @@ class Pose3d_Plane3d_Factor : public FactorT<Plane3d> {   // isam_plane3d.h:221-
   }
 };
 
+// Pose3d_Plane3d_Factor2 (isam_plane3d.h:314-424): the measurement is re-popped from the ground edge inside the residual
+class Pose3d_Plane3d_Factor2 : public Pose3d_Plane3d_Factor {
+  double _rays[6] = {0, 0, 0, 0, 0, 0};
+  bool _have_rays = false;
+ public:
+  Pose3d_Plane3d_Factor2(Pose3d_Node* pose, Plane3d_Node* plane, const Plane3d& measure, const Noise& noise, bool relative = false)
+      : Pose3d_Plane3d_Factor(pose, plane, measure, noise, relative) {}
+  // precompute_edge_ray (:358-370): invK (row-major 3x3, float) times the homogeneous end points of ONE ground segment
+  // (x1 y1 x2 y2, pixels), computed in float and widened to double as upstream; call before Slam::add_factor
+  void precompute_edge_ray(const float invK[9], const float seg[4]) {
+    for (int k = 0; k < 2; k++)
+      for (int i = 0; i < 3; i++) _rays[3 * k + i] = (double)(invK[i * 3] * seg[2 * k] + invK[i * 3 + 1] * seg[2 * k + 1] + invK[i * 3 + 2] * 1.0f);
+    _have_rays = true;
+  }
+  int _attach(pus_handle h) {
+    if (!_have_rays) throw std::runtime_error("Pose3d_Plane3d_Factor2: call precompute_edge_ray() before add_factor()");
+    Vector4d v = _measure.vector(); double a[4] = {v(0), v(1), v(2), v(3)};
+    std::vector<double> si = _noise.packed();
+    int f = pus_add_pose_plane2(h, _nodes[0]->unique_id(), _nodes[1]->unique_id(), a, _rays, si.data()); detail::check(f);
+    static_cast<Plane3d_Node*>(_nodes[1])->_mark_initialized();
+    return f;
+  }
+};
+
 // robust costs (ISAM/include/isam/robust.h:101-118); Slam::set_cost_function takes these tags
 struct cost_func_t { int kind; double b; };
 inline cost_func_t cost_huber_tag(double b) { return cost_func_t{1, b}; }

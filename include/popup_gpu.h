@@ -122,6 +122,11 @@ int pus_add_odometry(pus_handle h, int pose1, int pose2, const double* xyzypr, c
  * (isam_plane3d.h:221-308; Mapping.cpp:513,523). Initialises the plane on first sight (:252-264). */
 int pus_add_pose_plane(pus_handle h, int pose, int plane, const double* meas_abcd, const double* sqrtinf_ut6);
 /* Plane3d_Factor(plane, prior, noise) + add_factor  (isam_plane3d.h:428-474; Mapping.cpp:502-503) */
+/* Pose3d_Plane3d_Factor2 (pop_planar_slam/src/isam_plane3d.h:314-424): like pus_add_pose_plane, but the residual
+ * re-pops the measured wall plane from the two precomputed ground-edge rays (sensor frame, rays6 = r0, r1 as
+ * precompute_edge_ray :358-370 forms them: invK * (x, y, 1)) with the CURRENT pose on every evaluation
+ * (get_wall_plane_equation, isam_plane3d.cpp:20-55); meas4 only initialises an un-initialised plane node. */
+int pus_add_pose_plane2(pus_handle h, int pose, int plane, const double* meas4, const double* rays6, const double* sqrtinf_ut6);
 int pus_add_plane_prior(pus_handle h, int plane, const double* abcd, const double* sqrtinf_ut6);
 /* bulk forms (same semantics, applied in array order); out_fids may be NULL; returns first fid */
 int pus_add_odometry_bulk(pus_handle h, int n, const int* pose1, const int* pose2, const double* xyzypr,

@@ -106,6 +106,12 @@ int orc_add_pose_plane(void* h, int pose, int plane, const double* m, const doub
   if (r < 0) g_err = S(h)->last_error;
   return r;
 }
+int orc_add_pose_plane2(void* h, int pose, int plane, const double* m, const double* rays, const double* si) {
+  if (!valid_node(S(h), pose, NODE_POSE) || !valid_node(S(h), plane, NODE_PLANE)) { g_err = "bad node id"; return -1; }
+  int r = S(h)->add_pose_plane2(pose, plane, m, rays, si);
+  if (r < 0) g_err = S(h)->last_error;
+  return r;
+}
 int orc_add_plane_prior(void* h, int plane, const double* m, const double* si) {
   if (!valid_node(S(h), plane, NODE_PLANE)) { g_err = "bad plane id"; return -1; }
   return S(h)->add_plane_prior(plane, m, si);

@@ -331,6 +331,40 @@ inline void plane_log_error(const Plane& l, const Plane& m, double e[3]) {
   e[0] = ax[0] * angle; e[1] = ax[1] * angle; e[2] = ax[2] * angle;
 }
 
+// get_wall_plane_equation  pop_planar_slam/src/isam_plane3d.cpp:20-55 (with ray_plane_interact :14-18) for ONE
+// segment (two rays, 3 x 2 column layout of ground_edge_ray): output is not normalised.
+inline void wall_plane_from_rays(const double rays[6], const double T[16], double out[4]) {
+  // ground_plane_sensor = transToWorld^T * (0,0,-1,0)
+  const double gw[4] = {0, 0, -1, 0};
+  double gs[4];
+  for (int i = 0; i < 4; i++) gs[i] = T[0 * 4 + i] * gw[0] + T[1 * 4 + i] * gw[1] + T[2 * 4 + i] * gw[2] + T[3 * 4 + i] * gw[3];
+  double P[2][3];
+  for (int k = 0; k < 2; k++) {
+    const double* r = rays + 3 * k;
+    const double frac = -gs[3] / (gs[0] * r[0] + gs[1] * r[1] + gs[2] * r[2]);
+    for (int i = 0; i < 3; i++) P[k][i] = frac * r[i];
+  }
+  const double t1[3] = {P[1][0] - P[0][0], P[1][1] - P[0][1], P[1][2] - P[0][2]};
+  const double t2[3] = {gs[0], gs[1], gs[2]};
+  const double nrm[3] = {t1[1] * t2[2] - t1[2] * t2[1], t1[2] * t2[0] - t1[0] * t2[2], t1[0] * t2[1] - t1[1] * t2[0]};
+  out[0] = nrm[0]; out[1] = nrm[1]; out[2] = nrm[2];
+  out[3] = -(nrm[0] * P[0][0] + nrm[1] * P[0][1] + nrm[2] * P[0][2]);
+}
+
+// Pose3d_Plane3d_Factor2::basic_error  isam_plane3d.h:375-419 (_base == NULL): the measured plane is re-popped from
+// the precomputed ground-edge rays with the current pose (:384-386: row 0, 4-normalised), then the same log map.
+inline void pose_plane2_basic_error(const Pose& pose, const Plane& global_plane, const double rays[6], double e[3]) {
+  double T[16];
+  pose_wTo(pose, T);
+  Plane local = plane_transform_T(T, global_plane);
+  double raw[4];
+  wall_plane_from_rays(rays, T, raw);
+  Plane meas;
+  std::memcpy(meas.v, raw, sizeof(raw));
+  normalize4(meas.v);
+  plane_log_error(local, meas, e);
+}
+
 // Pose3d_Plane3d_Factor::basic_error  isam_plane3d.h:271-304 (useRelative=false,
 // Mapping.cpp:21 => _base == NULL)
 inline void pose_plane_basic_error(const Pose& pose, const Plane& global_plane, const Plane& meas, double e[3]) {

@@ -55,6 +55,8 @@ struct Factor {
   int dim = 3;
   double meas[6] = {0, 0, 0, 0, 0, 0};  // plane: abcd (normalised) ; pose: x,y,z,yaw,pitch,roll
   double sqrtinf[36];                   // dim x dim row-major, upper triangular
+  bool has_rays = false;                // Pose3d_Plane3d_Factor2: measurement re-popped from two ground-edge rays
+  double rays[6] = {0, 0, 0, 0, 0, 0};
 };
 
 // ISAM/include/isam/Properties.h:86-109 defaults
@@ -181,6 +183,15 @@ class Slam {
     return (int)factors.size() - 1;
   }
 
+  // Pose3d_Plane3d_Factor2  isam_plane3d.h:314-424 (precompute_edge_ray :358-370 supplies the two rays)
+  int add_pose_plane2(int pose, int plane, const double meas4[4], const double rays6[6], const double* sqrtinf_ut) {
+    int fid = add_pose_plane(pose, plane, meas4, sqrtinf_ut);
+    if (fid < 0) return fid;
+    factors[fid].has_rays = true;
+    std::memcpy(factors[fid].rays, rays6, 6 * sizeof(double));
+    return fid;
+  }
+
   // Plane3d_Factor  isam_plane3d.h:428-474 ; initialize :443-448
   int add_plane_prior(int plane, const double meas4[4], const double* sqrtinf_ut) {
     Factor f; f.kind = F_PLANE_PRIOR; f.n_nodes = 1; f.nodes[0] = plane; f.dim = 3;
@@ -246,7 +257,8 @@ class Slam {
         const Node& a = nodes[f.nodes[0]];
         const Node& b = nodes[f.nodes[1]];
         Plane m; std::memcpy(m.v, f.meas, 4 * sizeof(double));
-        pose_plane_basic_error(s == ESTIMATE ? a.pose : a.pose0, s == ESTIMATE ? b.plane : b.plane0, m, e);
+        if (f.has_rays) pose_plane2_basic_error(s == ESTIMATE ? a.pose : a.pose0, s == ESTIMATE ? b.plane : b.plane0, f.rays, e);
+        else pose_plane_basic_error(s == ESTIMATE ? a.pose : a.pose0, s == ESTIMATE ? b.plane : b.plane0, m, e);
       } break;
       case F_PLANE_PRIOR: {
         const Node& a = nodes[f.nodes[0]];
@@ -350,7 +362,7 @@ class Slam {
     int ncols = 0;
     for (int k = 0; k < f.n_nodes; k++) { lf.nodes[k] = f.nodes[k]; lf.ndim[k] = node_dim(nodes[f.nodes[k]].kind); ncols += lf.ndim[k]; }
     double r[6];
-    if (jac_mode == JAC_NUMERIC) {
+    if (jac_mode == JAC_NUMERIC || f.has_rays) {   // (Factor2 has no independent closed form here: numericalDiff as upstream)
       numerical_jacobian(f, lf.H, ncols);
       error(f, LINPOINT, r);  // Factor::jacobian Factor.h:127-128 (after numericalDiff)
     } else {

@@ -191,6 +191,12 @@ class GraphAPI:
     def add_pose_plane(self, pose, plane, meas4, sqrtinf6):
         return self._chk(self._f("add_pose_plane")(self.h, int(pose), int(plane), _dp(_f64(meas4, (4,))), _dp(_f64(sqrtinf6, (6,)))))
 
+    def add_pose_plane2(self, pose, plane, meas4, rays6, sqrtinf6):
+        """Pose3d_Plane3d_Factor2: measurement re-popped from two ground-edge rays inside the residual."""
+        fn = self._f("add_pose_plane2")
+        fn.argtypes = [C.c_void_p, C.c_int, C.c_int, c_double_p, c_double_p, c_double_p]
+        return self._chk(fn(self.h, int(pose), int(plane), _dp(_f64(meas4, (4,))), _dp(_f64(rays6, (6,))), _dp(_f64(sqrtinf6, (6,)))))
+
     def add_plane_prior(self, plane, abcd, sqrtinf6):
         return self._chk(self._f("add_plane_prior")(self.h, int(plane), _dp(_f64(abcd, (4,))), _dp(_f64(sqrtinf6, (6,)))))
 

@@ -185,7 +185,8 @@ static int upload(Solver* s) {
     d.SP = c.SP; d.inv_SP = 1.0 / (double)c.SP; d.ldmc = 6 * c.nc_pad; d.n_upart = c.n_upart; d.n_ypart = c.n_ypart; d.nce = c.nce; d.ngrp = c.ngrp;
 #define UP(field) if (s->dupload(&d.field, c.field, &bytes) < 0) return -1
     UP(pp_pose); UP(pp_plane); UP(pp_ptr); UP(pp_end); UP(pm2pl); UP(pm_part); UP(ypart_ptr); UP(tile_ptr); UP(blk_part_ptr);
-    UP(grp_of_slot); UP(pp_meas); UP(pp_sinf);
+    UP(grp_of_slot); UP(pp_meas); UP(pp_sinf); UP(pp_rays); UP(pp_kind);
+    d.n_f2 = c.n_f2;
     UP(pl2pm); UP(pl_ptr); UP(pl_plane); UP(pl_pose); UP(pl_part); UP(upart_ptr); UP(heavy); UP(huge);
     d.n_heavy = c.n_heavy; d.n_huge = c.n_huge;
     UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pnbr); UP(pf_meas); UP(pf_sinf);
@@ -546,6 +547,7 @@ static int chk(Solver* s, int r) { if (r < 0) g_err = s->g.err; return r; }
 int pus_add_pose_prior(pus_handle h, int p, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_pose_prior(p, m, si)); }
 int pus_add_odometry(pus_handle h, int a, int b, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_odometry(a, b, m, si)); }
 int pus_add_pose_plane(pus_handle h, int p, int l, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_pose_plane(p, l, m, si)); }
+int pus_add_pose_plane2(pus_handle h, int p, int l, const double* m, const double* rays, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_pose_plane2(p, l, m, rays, si)); }
 int pus_add_plane_prior(pus_handle h, int l, const double* m, const double* si) { NEED(h); return chk(SV(h), SV(h)->g.add_plane_prior(l, m, si)); }
 int pus_add_odometry_bulk(pus_handle h, int n, const int* a, const int* b, const double* m, const double* si, int* out) {
   NEED(h);

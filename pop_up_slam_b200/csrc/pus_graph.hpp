@@ -48,6 +48,8 @@ struct HFactor {
   int dim = 3;
   double meas[6] = {0, 0, 0, 0, 0, 0};
   double sinf[21];  // packed upper-triangular
+  bool has_rays = false;   // Pose3d_Plane3d_Factor2: the measured plane is re-popped from two ground-edge rays (sensor frame)
+  double rays[6] = {0, 0, 0, 0, 0, 0};
 };
 
 struct Graph {
@@ -115,6 +117,14 @@ struct Graph {
     }
     return push_factor(f);
   }
+  // Pose3d_Plane3d_Factor2 (isam_plane3d.h:314-424): same nodes / initialisation, plus the precomputed rays (:358-370)
+  int add_pose_plane2(int pose, int plane, const double* m, const double* rays6, const double* si) {
+    const int f = add_pose_plane(pose, plane, m, si);
+    if (f < 0) return f;
+    factors[f].has_rays = true;
+    std::memcpy(factors[f].rays, rays6, 6 * sizeof(double));
+    return f;
+  }
   int add_plane_prior(int plane, const double* m, const double* si) {
     if (!ok_node(plane, NODE_PLANE)) { err = "add_plane_prior: bad plane id"; return -1; }
     HFactor f; f.kind = F_PLANE_PRIOR; f.n_nodes = 1; f.nodes[0] = plane; f.dim = 3;
@@ -162,7 +172,9 @@ struct Compiled {
   // pose-plane edges, pose-major
   // (slot-indexed: every 16-pose block's edges are padded to whole 32-edge tiles; pad slots have pp_pose = -1)
   std::vector<int> pp_fid, pp_pose, pp_plane, pp_ptr, pm2pl, pm_part, ypart_ptr, tile_ptr, blk_part_ptr, grp_of_slot;
-  std::vector<double> pp_meas, pp_sinf;
+  std::vector<double> pp_meas, pp_sinf, pp_rays;   // pp_rays: [slots][6] when any edge is a Factor2 (else one dummy entry)
+  std::vector<int> pp_kind;                        // 1 = Factor2 (uses pp_rays), else 0
+  int n_f2 = 0;
   // plane-major view
   std::vector<int> pl2pm, pl_ptr, pl_plane, pl_pose, pl_part, upart_ptr, pp_end, heavy, huge;
   int ntile_pl = 0;
@@ -256,6 +268,7 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     c.pp_fid.assign(slots, -1); c.pp_pose.assign(slots, -1); c.pp_plane.assign(slots, 0);
     c.pp_meas.assign((size_t)slots * 4, 0.0); c.pp_sinf.assign((size_t)slots * 6, 0.0);
     for (int s2 = 0; s2 < slots; s2++) c.pp_meas[(size_t)s2 * 4] = 1.0;
+    c.pp_rays.assign(1, 0.0); c.pp_kind.assign(1, 0); c.n_f2 = 0;
     std::vector<int> fill(c.pp_ptr.begin(), c.pp_ptr.begin() + N);
     for (int i = 0; i < E; i++) {
       const HFactor& F = g.factors[ppf[order[i]]];
@@ -265,6 +278,11 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
       c.pp_pose[e] = p;
       c.pp_plane[e] = c.node_idx[F.nodes[1]];
       std::memcpy(&c.pp_meas[(size_t)e * 4], F.meas, 4 * sizeof(double));
+      if (F.has_rays) {
+        if (c.pp_rays.size() < (size_t)slots * 6) { c.pp_rays.assign((size_t)slots * 6, 0.0); c.pp_kind.assign(slots, 0); }
+        std::memcpy(&c.pp_rays[(size_t)e * 6], F.rays, 6 * sizeof(double));
+        c.pp_kind[e] = 1; c.n_f2++;
+      }
       std::memcpy(&c.pp_sinf[(size_t)e * 6], F.sinf, 6 * sizeof(double));
     }
     c.pp_end.assign(N, 0);

@@ -66,7 +66,9 @@ struct DevGraph {
   double *pose_lin, *pose_trial, *pose_init, *plane_lin, *plane_trial, *plane_init;
   // pose-plane edges (pose-major) and plane-major view
   const int *pp_pose, *pp_plane, *pp_ptr, *pp_end, *pm2pl, *pm_part, *ypart_ptr, *tile_ptr, *blk_part_ptr, *grp_of_slot;
-  const double *pp_meas, *pp_sinf;
+  const double *pp_meas, *pp_sinf, *pp_rays;
+  const int* pp_kind;
+  int n_f2;   // number of Pose3d_Plane3d_Factor2 edges (0: pp_rays / pp_kind are dummies)
   const int *pl2pm, *pl_ptr, *pl_plane, *pl_pose, *pl_part, *upart_ptr, *heavy, *huge;
   int n_heavy, n_huge;
   // pose factors / plane priors
@@ -498,6 +500,14 @@ __device__ __forceinline__ double* gj_invert_smem(double* Mc, double* Mn, double
   return Mc;
 }
 
+// Pose3d_Plane3d_Factor2 edges are rare (disabled in the shipped demo): keep their extra arithmetic out of the
+// register allocation of the common path
+__device__ __noinline__ void pose_plane2_linearize(const double* pose, const double* plane, const double* rays, const double* sinf,
+                                                   int robust_kind, double robust_b, double* r, double* Jp, double* Jl) {
+  const double unit[4] = {1, 0, 0, 0};
+  pose_plane_linearize(pose, plane, unit, sinf, robust_kind, robust_b, r, Jp, Jl, rays);
+}
+
 struct Phase {
   const DevGraph& G;
   Ctx& c;
@@ -530,7 +540,10 @@ struct Phase {
         for (int i = 0; i < 4; i++) m[i] = G.pp_meas[(size_t)e * 4 + i];
         for (int i = 0; i < 6; i++) si[i] = G.pp_sinf[(size_t)e * 6 + i];
         double r[3], Jp[18], Jl[9];
-        pose_plane_linearize(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, Jp, Jl);
+        if (G.n_f2 > 0 && G.pp_kind[e])   // Factor2: measurement re-popped from the edge's rays (kept out of line)
+          pose_plane2_linearize(pose, pl, G.pp_rays + (size_t)e * 6, si, G.prm.robust_kind, G.prm.robust_b, r, Jp, Jl);
+        else
+          pose_plane_linearize(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, Jp, Jl);
         double* w = G.W + (size_t)tile * kWStride + lane;
         int s = G.pm2pl[e];
         double* wt = G.Wt + (size_t)(s >> 5) * kWStride + (s & 31);
@@ -676,7 +689,10 @@ struct Phase {
       for (int i = 0; i < 4; i++) pl[i] = ldc(LV + (size_t)l * 4 + i);
       for (int i = 0; i < 4; i++) m[i] = G.pp_meas[(size_t)e * 4 + i];
       for (int i = 0; i < 6; i++) si[i] = G.pp_sinf[(size_t)e * 6 + i];
-      pose_plane_linearize(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, nullptr);
+      if (G.n_f2 > 0 && G.pp_kind[e])
+        pose_plane2_linearize(pose, pl, G.pp_rays + (size_t)e * 6, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, nullptr);
+      else
+        pose_plane_linearize(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, nullptr);
       acc += r[0] * r[0] + r[1] * r[1] + r[2] * r[2];
     }
     for (int f = tid_team(); f < G.Epf; f += nthr_team()) {

@@ -233,7 +233,7 @@ PUS_HD double robustify(int kind, double b, double& r) {
 // ---- log-map between a (unit) plane l and a measured plane m, with derivative wrt l ----
 // e = axis*angle of dq = q(l) * conj(q(m)), angle wrapped to (-pi,pi] (isam_plane3d.h:285-294;
 // Eigen::AngleAxisd(Quaterniond), atan2 form).  G4 (3x4 row-major) = de/dl, or nullptr.
-PUS_HD void plane_log(const double* l, const double* m, double* e, double* G4) {
+PUS_HD void plane_log(const double* l, const double* m, double* e, double* G4, double* G4m = nullptr) {
   const double mw = m[3];
   double a0 = mw * l[0] + (m[1] * l[2] - m[2] * l[1]) - l[3] * m[0];
   double a1 = mw * l[1] + (m[2] * l[0] - m[0] * l[2]) - l[3] * m[1];
@@ -269,6 +269,60 @@ PUS_HD void plane_log(const double* l, const double* m, double* e, double* G4) {
     double g2 = mw * Da[2] + (Da[0] * m[1] - Da[1] * m[0]) + Dw * m[2];
     double g3 = -(Da[0] * m[0] + Da[1] * m[1] + Da[2] * m[2]) + Dw * mw;
     G4[i * 4 + 0] = sgn * g0; G4[i * 4 + 1] = sgn * g1; G4[i * 4 + 2] = sgn * g2; G4[i * 4 + 3] = sgn * g3;
+    if (G4m) {
+      // de/dm = D * sgn * N(l),  N = [[ -[lv]x - lw I , lv ],[ lv^T , lw ]]   (a = mw lv + mv x lv - lw mv, w = mv.lv + mw lw)
+      // (Da^T [lv]x) = (Da1*l2 - Da2*l1, Da2*l0 - Da0*l2, Da0*l1 - Da1*l0)
+      const double n0 = -(Da[1] * l[2] - Da[2] * l[1]) - l[3] * Da[0] + Dw * l[0];
+      const double n1 = -(Da[2] * l[0] - Da[0] * l[2]) - l[3] * Da[1] + Dw * l[1];
+      const double n2 = -(Da[0] * l[1] - Da[1] * l[0]) - l[3] * Da[2] + Dw * l[2];
+      const double n3 = (Da[0] * l[0] + Da[1] * l[1] + Da[2] * l[2]) + Dw * l[3];
+      G4m[i * 4 + 0] = sgn * n0; G4m[i * 4 + 1] = sgn * n1; G4m[i * 4 + 2] = sgn * n2; G4m[i * 4 + 3] = sgn * n3;
+    }
+  }
+}
+
+// ---- Pose3d_Plane3d_Factor2 (isam_plane3d.h:314-424): the measured wall plane is re-popped from the two precomputed
+// ground-edge rays with the CURRENT pose inside the residual: get_wall_plane_equation (isam_plane3d.cpp:20-55, double):
+//   gs = wTo^T (0,0,-1,0) = (-R[2,:]^T, -t_z) ;  P_k = -gs_d / (gs_n . r_k) r_k ;  n = (P1 - P0) x gs_n ;  d = -n . P0
+// followed by the 4-normalisation of isam_plane3d.h:385.  rays = (r0, r1).  m4 = the normalised plane; when dm (4x6
+// row-major) is given it receives d m / d (delta_t, delta_phi) for the pose exmap (t += dt, R <- R Exp(dphi)).
+PUS_HD void popup_plane_from_rays(const double* R, const double* t, const double* rays, double* m4, double* dm) {
+  const double g[3] = {-R[6], -R[7], -R[8]}, h = t[2];
+  const double* r0 = rays;
+  const double* r1 = rays + 3;
+  const double s0 = g[0] * r0[0] + g[1] * r0[1] + g[2] * r0[2], s1 = g[0] * r1[0] + g[1] * r1[1] + g[2] * r1[2];
+  const double f0 = h / s0, f1 = h / s1;
+  const double P0[3] = {f0 * r0[0], f0 * r0[1], f0 * r0[2]}, P1[3] = {f1 * r1[0], f1 * r1[1], f1 * r1[2]};
+  const double v[3] = {P1[0] - P0[0], P1[1] - P0[1], P1[2] - P0[2]};
+  const double n[3] = {v[1] * g[2] - v[2] * g[1], v[2] * g[0] - v[0] * g[2], v[0] * g[1] - v[1] * g[0]};
+  const double d = -(n[0] * P0[0] + n[1] * P0[1] + n[2] * P0[2]);
+  const double raw[4] = {n[0], n[1], n[2], d};
+  const double nn = sqrt(raw[0] * raw[0] + raw[1] * raw[1] + raw[2] * raw[2] + raw[3] * raw[3]);
+  for (int i = 0; i < 4; i++) m4[i] = raw[i] / nn;
+  if (!dm) return;
+  double draw[4][6];
+  for (int i = 0; i < 4; i++) for (int k = 0; k < 6; k++) draw[i][k] = 0.0;
+  for (int k = 2; k < 6; k++) {   // delta_t_z (k = 2) and delta_phi (k = 3..5); delta_t_x, delta_t_y leave the plane unchanged
+    double dh = 0, dg[3] = {0, 0, 0};
+    if (k == 2) dh = 1.0;
+    else {  // dg = g x e_j
+      const int j = k - 3;
+      const double ej[3] = {j == 0 ? 1.0 : 0.0, j == 1 ? 1.0 : 0.0, j == 2 ? 1.0 : 0.0};
+      dg[0] = g[1] * ej[2] - g[2] * ej[1]; dg[1] = g[2] * ej[0] - g[0] * ej[2]; dg[2] = g[0] * ej[1] - g[1] * ej[0];
+    }
+    const double c0 = dh / s0 - h * (r0[0] * dg[0] + r0[1] * dg[1] + r0[2] * dg[2]) / (s0 * s0);
+    const double c1 = dh / s1 - h * (r1[0] * dg[0] + r1[1] * dg[1] + r1[2] * dg[2]) / (s1 * s1);
+    const double dP0[3] = {c0 * r0[0], c0 * r0[1], c0 * r0[2]}, dP1[3] = {c1 * r1[0], c1 * r1[1], c1 * r1[2]};
+    const double dv[3] = {dP1[0] - dP0[0], dP1[1] - dP0[1], dP1[2] - dP0[2]};
+    const double dn[3] = {dv[1] * g[2] - dv[2] * g[1] + v[1] * dg[2] - v[2] * dg[1],
+                          dv[2] * g[0] - dv[0] * g[2] + v[2] * dg[0] - v[0] * dg[2],
+                          dv[0] * g[1] - dv[1] * g[0] + v[0] * dg[1] - v[1] * dg[0]};
+    const double dd = -(dn[0] * P0[0] + dn[1] * P0[1] + dn[2] * P0[2]) - (n[0] * dP0[0] + n[1] * dP0[1] + n[2] * dP0[2]);
+    draw[0][k] = dn[0]; draw[1][k] = dn[1]; draw[2][k] = dn[2]; draw[3][k] = dd;
+  }
+  for (int k = 0; k < 6; k++) {   // (I - m m^T) / |raw| * draw
+    const double mk = m4[0] * draw[0][k] + m4[1] * draw[1][k] + m4[2] * draw[2][k] + m4[3] * draw[3][k];
+    for (int i = 0; i < 4; i++) dm[i * 6 + k] = (draw[i][k] - m4[i] * mk) / nn;
   }
 }
 
@@ -283,10 +337,15 @@ PUS_HD void weight3(const double* s, double* v0, double* v1, double* v2) {
 // Pose-plane edge: weighted, robustified residual r[3] and (optionally) Jp[18] (3x6 row-major,
 // columns = delta_t, delta_phi) and Jl[9] (3x3, plane tangent).  SURVEY.md Appendix A.1.
 // pose == nullptr => plane prior (R = I, t = 0; Jp untouched).
+// rays != nullptr => Pose3d_Plane3d_Factor2: `meas` is ignored, the measured plane is re-popped from the rays with the
+// current pose (popup_plane_from_rays) and its dependence on the pose enters Jp.
 PUS_HD void pose_plane_linearize(const double* pose, const double* plane, const double* meas, const double* sinf,
-                                 int robust_kind, double robust_b, double* r, double* Jp, double* Jl) {
+                                 int robust_kind, double robust_b, double* r, double* Jp, double* Jl, const double* rays = nullptr) {
   double R[9] = {1, 0, 0, 0, 1, 0, 0, 0, 1}, t[3] = {0, 0, 0};
   if (pose) { quat_to_R(pose + 3, R); t[0] = pose[0]; t[1] = pose[1]; t[2] = pose[2]; }
+  double m2[4], dm[24], G4m[12];
+  const bool f2 = (rays != nullptr) && (pose != nullptr);
+  if (f2) { popup_plane_from_rays(R, t, rays, m2, (Jp != nullptr) ? dm : nullptr); meas = m2; }
   const double n0 = plane[0], n1 = plane[1], n2 = plane[2], d = plane[3];
   double u[4];
   u[0] = R[0] * n0 + R[3] * n1 + R[6] * n2;
@@ -297,7 +356,7 @@ PUS_HD void pose_plane_linearize(const double* pose, const double* plane, const 
   double l[4] = {u[0] / s, u[1] / s, u[2] / s, u[3] / s};
   double e[3], G4[12];
   const bool want_J = (Jl != nullptr);
-  plane_log(l, meas, e, want_J ? G4 : nullptr);
+  plane_log(l, meas, e, want_J ? G4 : nullptr, (want_J && f2) ? G4m : nullptr);
   r[0] = e[0]; r[1] = e[1]; r[2] = e[2];
   weight3(sinf, &r[0], &r[1], &r[2]);
   double wr[3];
@@ -318,6 +377,9 @@ PUS_HD void pose_plane_linearize(const double* pose, const double* plane, const 
     jp[i * 6 + 3] = g1 * u[2] - g2 * u[1];
     jp[i * 6 + 4] = g2 * u[0] - g0 * u[2];
     jp[i * 6 + 5] = g0 * u[1] - g1 * u[0];
+    if (f2 && Jp)   // + (de/dm) (dm/dpose)
+      for (int k = 2; k < 6; k++)
+        jp[i * 6 + k] += G4m[i * 4] * dm[k] + G4m[i * 4 + 1] * dm[6 + k] + G4m[i * 4 + 2] * dm[12 + k] + G4m[i * 4 + 3] * dm[18 + k];
     // GA = G * [[R^T,0],[t^T,1]]
     double ga[4];
     for (int j = 0; j < 3; j++) ga[j] = g0 * R[j * 3 + 0] + g1 * R[j * 3 + 1] + g2 * R[j * 3 + 2] + g3 * t[j];

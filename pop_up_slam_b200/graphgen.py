@@ -370,3 +370,14 @@ def configure(api, g, **overrides):
     props.update(overrides)
     api.set_properties(**props)
     api.set_robust(g.robust_kind, g.robust_b)
+
+
+def rays_from_measurement(T_pose, meas):
+    """Two ground-edge rays (sensor frame) for a Pose3d_Plane3d_Factor2: points on the intersection line of the
+    measured wall plane `meas` (sensor frame) with the ground plane z = 0 as seen from the camera pose `T_pose`
+    (what invK * (x, y, 1) of the wall's ground edge would give, up to scale)."""
+    gs = T_pose.T @ np.array([0.0, 0.0, -1.0, 0.0])
+    nm, dm = np.asarray(meas[:3], dtype=float), float(meas[3])
+    u = np.cross(nm, gs[:3])
+    p0 = (-dm * np.cross(gs[:3], u) - gs[3] * np.cross(u, nm)) / (u @ u)
+    return np.concatenate([p0 - 0.7 * u / np.linalg.norm(u), p0 + 0.9 * u / np.linalg.norm(u)])

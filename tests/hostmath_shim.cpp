@@ -7,6 +7,11 @@ void hm_pose_plane_linearize(const double* pose, const double* plane, const doub
                              double rb, double* r, double* Jp, double* Jl) {
   pose_plane_linearize(pose, plane, meas, sinf, rk, rb, r, Jp, Jl);
 }
+void hm_pose_plane2_linearize(const double* pose, const double* plane, const double* rays, const double* sinf, int rk,
+                              double rb, double* r, double* Jp, double* Jl) {
+  const double dummy[4] = {1, 0, 0, 0};
+  pose_plane_linearize(pose, plane, dummy, sinf, rk, rb, r, Jp, Jl, rays);
+}
 void hm_plane_prior_linearize(const double* plane, const double* meas, const double* sinf, int rk, double rb, double* r,
                               double* Jl) {
   pose_plane_linearize(nullptr, plane, meas, sinf, rk, rb, r, nullptr, Jl);

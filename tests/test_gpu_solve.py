@@ -197,6 +197,41 @@ def test_one_graph_spanning_ranks_emulated(cfg, world, kw):
     assert np.array_equal(apis[0].get_poses(infos[0]["pose_ids"]), apis[-1].get_poses(infos[-1]["pose_ids"]))   # bit-identical ranks
 
 
+def test_pose_plane_factor2_matches_oracle():
+    """Pose3d_Plane3d_Factor2 (isam_plane3d.h:314-424) -- every wall observation re-pops its measured
+    plane from two ground-edge rays with the current pose inside the residual; the ground-plane observations stay
+    ordinary factors.  Same LM trace and estimates as the oracle (numericalDiff there, closed form here), and the
+    saved graph names the factor as the reference does."""
+    g = gg.make_config(2, seed=6, n_poses=120, n_planes=30)
+    res = []
+    for api in (GpuGraphAPI(), OracleAPI()):
+        pose_ids = api.add_poses(g.poses_init)
+        plane_ids = api.add_planes(g.planes_init)
+        api.add_pose_prior(pose_ids[g.prior_pose], g.prior_meas, g.prior_sqrtinf)
+        api.add_odometry_bulk(pose_ids[g.odo_i], pose_ids[g.odo_j], g.odo_meas, g.odo_sqrtinf)
+        api.add_plane_prior(plane_ids[g.ground_plane], g.ground_meas, g.ground_sqrtinf)
+        n2 = 0
+        for e in range(g.n_pose_plane):
+            p, k = int(g.pp_pose[e]), int(g.pp_plane[e])
+            if k == g.ground_plane:
+                api.add_pose_plane(pose_ids[p], plane_ids[k], g.pp_meas[e], g.pp_sqrtinf[e])
+            else:
+                rays = gg.rays_from_measurement(geo.pose7_to_T(g.poses_truth[p]), g.pp_meas[e])
+                api.add_pose_plane2(pose_ids[p], plane_ids[k], g.pp_meas[e], rays, g.pp_sqrtinf[e])
+                n2 += 1
+        assert n2 > 500
+        gg.configure(api, g)
+        c0 = api.chi2()
+        it = api.batch_optimize()
+        res.append((api, dict(pose_ids=pose_ids, plane_ids=plane_ids), c0, it))
+    (gpu, ig, c0g, itg), (orc, io, c0o, ito) = res
+    assert abs(c0g - c0o) <= 1e-9 * c0o
+    assert itg == ito
+    assert np.array_equal(gpu.trace()["accepted"], orc.trace()["accepted"])
+    assert np.allclose(gpu.trace()["chi2_new"], orc.trace()["chi2_new"], rtol=1e-4)
+    compare(gpu, orc, ig, io)
+
+
 def test_gauss_newton_and_update_match_oracle():
     g = gg.make_config(2, seed=1)
     for which in ("gn", "update"):

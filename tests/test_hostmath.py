@@ -10,7 +10,7 @@ import pytest
 from oracle_api import OracleAPI
 import oracle_api as O
 from pop_up_slam_b200.capi import _dp
-from pop_up_slam_b200 import geometry as geo
+from pop_up_slam_b200 import geometry as geo, graphgen as gg
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 
@@ -26,6 +26,7 @@ def hm():
     dbl = C.c_double
     P = C.POINTER(C.c_double)
     lib.hm_pose_plane_linearize.argtypes = [P, P, P, P, C.c_int, dbl, P, P, P]
+    lib.hm_pose_plane2_linearize.argtypes = [P, P, P, P, C.c_int, dbl, P, P, P]
     lib.hm_plane_prior_linearize.argtypes = [P, P, P, C.c_int, dbl, P, P]
     lib.hm_pose_plane_residual.argtypes = [P, P, P, P, C.c_int, dbl, P]
     lib.hm_pose_factor_linearize.argtypes = [P, P, P, P, C.c_int, dbl, P, P, P]
@@ -155,3 +156,30 @@ def test_exmaps_match_oracle(hm):
         assert np.allclose(o7, O.pose_oplus(a, b), atol=1e-14)
         hm.hm_pose_ominus(_dp(a), _dp(b), _dp(o7))
         assert np.allclose(o7, O.pose_ominus(a, b), atol=1e-14)
+
+
+def test_pose_plane_factor2_matches_oracle(hm):
+    """Pose3d_Plane3d_Factor2 (measurement re-popped from two ground-edge rays inside the residual): the closed-form
+    pose Jacobian of the product header (incl. d measurement / d pose) against the oracle's numericalDiff of its own,
+    independent restatement of isam_plane3d.h:375-419 / isam_plane3d.cpp:20-55."""
+    rng = np.random.default_rng(5)
+    for trial in range(150):
+        R = geo.euler_to_R(rng.uniform(-3, 3), rng.uniform(-0.15, 0.15), rng.uniform(-0.15, 0.15)) @ gg.R_BASE
+        T = np.eye(4); T[:3, :3] = R; T[:3, 3] = [rng.uniform(-3, 3), rng.uniform(-3, 3), rng.uniform(0.8, 1.8)]
+        pose = geo.T_to_pose7(T)
+        th = rng.uniform(-np.pi, np.pi)
+        wall = geo.plane_normalize([np.cos(th), np.sin(th), 0.0, -rng.uniform(2.0, 6.0)])   # a vertical wall
+        plane = geo.plane_exmap(wall, rng.normal(0, 0.05, 3))
+        meas = geo.plane_exmap(geo.plane_to_local(T, wall), rng.normal(0, 0.02, 3))
+        rays = gg.rays_from_measurement(T, meas)
+        sinf = ut(rng, 3)
+        api = OracleAPI()
+        pid, lid = api.add_pose(pose), api.add_plane(plane)
+        fid = api.add_pose_plane2(pid, lid, meas, rays, sinf)
+        Hn, rn = api.factor_jacobian(fid, 0)
+        r, Jp, Jl = np.zeros(3), np.zeros(18), np.zeros(9)
+        hm.hm_pose_plane2_linearize(_dp(pose), _dp(plane), _dp(rays), _dp(sinf), 0, 1.0, _dp(r), _dp(Jp), _dp(Jl))
+        J = np.hstack([Jp.reshape(3, 6), Jl.reshape(3, 3)])
+        scale = max(1.0, np.abs(Hn).max())
+        assert np.allclose(r, rn, atol=1e-11 * max(1, np.abs(rn).max())), (r, rn)
+        assert np.abs(J - Hn).max() <= 2e-5 * scale, (trial, np.abs(J - Hn).max(), scale)
