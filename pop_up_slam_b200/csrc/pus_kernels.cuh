@@ -5,10 +5,13 @@
 //   linearise   every residual + closed-form 3x6 / 3x3 (6x6) Jacobian blocks in one sweep, W = Jp^T Jl
 //               written in both pose-major and plane-major warp tiles ([tile][18][32] doubles)
 //   assemble    Hpp, gp (per pose), Hll, gl (per plane) by fixed-order gathers (no float atomics)
-//   Schur       Hll^-1 (3x3), dense 96x96 diagonal blocks of S = Hpp - W Hll^-1 W^T inverted in shared
-//               memory, Galerkin coarse operator on piecewise-linear trajectory modes inverted in HBM
+//   Schur       Hll^-1 (3x3); dense 96x96 diagonal blocks of S = Hpp - W Hll^-1 W^T built by pose-pair ownership and
+//               inverted in shared memory (blocked Gauss-Jordan, rank-8 updates on the FP64 tensor cores);
+//               Galerkin coarse operator on piecewise-linear trajectory modes, assembled output-stationary and
+//               inverted in HBM (48-wide pivots, panel chunks staged by bulk async copies, rank-48 DMMA updates)
 //   PCG         implicit-Schur operator: plane-major sweep (W^T p), plane solve, pose-major sweep (W v),
-//               two-level additive preconditioner, deterministic segmented reductions
+//               two-level additive preconditioner, deterministic segmented reductions; on large graphs the W / Wt
+//               tiles and the dense preconditioner blocks stream through shared memory by cp.async.bulk + mbarrier
 //   update      exmap of every vertex, trial chi2, accept / reject, lambda rule -- all on device
 // Control flow follows Optimizer::levenberg_marquardt / gauss_newton / relinearize of the reference
 // (pop_planar_slam/Thirdparty/isam/isamlib/Optimizer.cpp:371-467, 286-366, 114-185).
