@@ -14,20 +14,19 @@
 #include "pus_graph.hpp"
 
 namespace pus {
-// the device code is instantiated twice: kplain = the single-GPU kernel (spanning hooks compiled out), kspan = one
-// graph spanning ranks.  Both define the same types with the same layout; the host side uses kplain's names.
+// the device code is instantiated twice: kplain (here) = the single-GPU kernel, spanning hooks compiled out; kspan
+// (pus_span.cu) = one graph spanning ranks.  Both define the same types with the same layout; the host uses kplain's.
 namespace kplain {
 #define PUS_NO_SPAN 1
 #include "pus_kernels.cuh"
 #include "pus_driver.cuh"
 #undef PUS_NO_SPAN
 }  // namespace kplain
-namespace kspan {
-#include "pus_kernels.cuh"
-#include "pus_driver.cuh"
-}  // namespace kspan
 using namespace kplain;
-static_assert(sizeof(kplain::DevGraph) == sizeof(kspan::DevGraph), "the two device instantiations share one layout");
+// the second instantiation (pus::kspan, spanning hooks compiled in) lives in pus_span.cu
+void* span_kernel_ptr();
+size_t span_devgraph_bytes();
+cudaError_t span_kernel_prepare();
 
 // ---------------------------------------------------------------------------------------------
 // host engine
@@ -159,7 +158,8 @@ static int ensure_device(Solver* s) {
     CUDA_OK(cudaGetDeviceProperties(&p, s->device));
     s->num_sms = p.multiProcessorCount;
     CUDA_OK(cudaFuncSetAttribute(kplain::lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
-    CUDA_OK(cudaFuncSetAttribute(kspan::lm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CUDA_OK(span_kernel_prepare());
+    if (span_devgraph_bytes() != sizeof(DevGraph)) { g_err = "device-code instantiations disagree on the DevGraph layout"; return -1; }
   }
   return 0;
 }
@@ -351,7 +351,7 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
   void* args[] = {(void*)&a0, (void*)&a1, (void*)&a2, (void*)&a3};
   bool spanning = false;
   for (int i = 0; i < n; i++) spanning = spanning || (hg[i].span_w > 1);
-  void* kfn = spanning ? (void*)kspan::lm_kernel : (void*)kplain::lm_kernel;
+  void* kfn = spanning ? span_kernel_ptr() : (void*)kplain::lm_kernel;
   cudaError_t le = cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kThreads), args, kSmemBytes, s0->stream);
   if (le != cudaSuccess) { g_err = std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(le); if (d_tmp) cudaFree(d_tmp); return -1; }
   CUDA_OK(cudaEventRecord(s0->ev1, s0->stream));
