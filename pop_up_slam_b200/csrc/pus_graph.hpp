@@ -240,11 +240,14 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   c.Epl = (int)ppf.size();
   const int E = c.Epl;
   c.nblk = (N + kBlockPoses - 1) / kBlockPoses;
-  std::vector<int> order(E);
-  for (int i = 0; i < E; i++) order[i] = i;
-  std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
-    return c.node_idx[g.factors[ppf[a]].nodes[0]] < c.node_idx[g.factors[ppf[b]].nodes[0]];
-  });
+  // stable counting sort by pose index (keys gathered once: the comparison sort chased the factor records)
+  std::vector<int> order(E), key(E);
+  {
+    std::vector<int> start(N + 1, 0);
+    for (int i = 0; i < E; i++) { key[i] = c.node_idx[g.factors[ppf[i]].nodes[0]]; start[key[i] + 1]++; }
+    for (int p = 0; p < N; p++) start[p + 1] += start[p];
+    for (int i = 0; i < E; i++) order[start[key[i]]++] = i;
+  }
   c.pp_ptr.assign(N + 1, 0);
   c.tile_ptr.assign(c.nblk + 1, 0);
   {
@@ -310,10 +313,13 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   // ---- plane-major view (slots of its own: dense, E real entries then padding) ----
   const int pslots = (E + kTile - 1) / kTile * kTile;
   c.ntile_pl = pslots / kTile;
-  std::vector<int> pord;
-  pord.reserve(E);
-  for (int e = 0; e < slots; e++) if (c.pp_pose[e] >= 0) pord.push_back(e);
-  std::stable_sort(pord.begin(), pord.end(), [&](int a, int b) { return c.pp_plane[a] < c.pp_plane[b]; });
+  std::vector<int> pord(E);   // live slots in slot order, stably counting-sorted by plane
+  {
+    std::vector<int> start(M + 1, 0);
+    for (int e = 0; e < slots; e++) if (c.pp_pose[e] >= 0) start[c.pp_plane[e] + 1]++;
+    for (int l = 0; l < M; l++) start[l + 1] += start[l];
+    for (int e = 0; e < slots; e++) if (c.pp_pose[e] >= 0) pord[start[c.pp_plane[e]]++] = e;
+  }
   c.pl2pm.assign(pslots, -1); c.pl_plane.assign(pslots, -1); c.pl_pose.assign(pslots, 0); c.pl_part.assign(pslots, -1);
   c.pm2pl.assign(slots, -1);
   c.pl_ptr.assign(M + 1, 0); c.upart_ptr.assign(M + 1, 0);
@@ -434,12 +440,10 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
         int nd = cand[q];
         if (nd < 0 || nd <= last) continue;
         // slots of plane l supporting node nd: poses in ((nd-1)*SP, (nd+1)*SP)
-        int lo = s, hi = s;
-        // lo: first slot with pose > (nd-1)*SP ; since slots are pose-sorted within the plane, scan
-        lo = s0;
-        while (lo < s1 && c.pl_pose[lo] <= (nd - 1) * SPc) lo++;
-        hi = lo;
-        while (hi < s1 && c.pl_pose[hi] < (nd + 1) * SPc) hi++;
+        // slots are pose-sorted within the plane: lo = first slot with pose > (nd-1)*SP, hi = first with pose >= (nd+1)*SP
+        const int* pb = c.pl_pose.data();
+        const int lo = (int)(std::upper_bound(pb + s0, pb + s1, (nd - 1) * SPc) - pb);
+        const int hi = (int)(std::lower_bound(pb + lo, pb + s1, (nd + 1) * SPc) - pb);
         c.ce_node.push_back(nd); c.ce_plane.push_back(l); c.ce_lo.push_back(lo); c.ce_hi.push_back(hi);
         last = nd;
       }
