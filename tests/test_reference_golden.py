@@ -1,0 +1,130 @@
+"""Checks against tests/golden/reference_build.json: outputs of the reference's OWN code (oracle/_ref = unmodified iSAM +
+isam_plane3d sources compiled against API shims; generator tools/make_ref_golden.py).  The fixtures travel with the repo,
+so these tests need neither the reference checkout nor the _ref library at run time.
+
+CPU (not gpu): the oracle restatement reproduces every vector -- per-factor error() / numericalDiff Jacobians, manifold
+operations, and whole LM runs on BASELINE configs 1, 2, a reduced Huber corridor and the full-size bench workload.
+GPU: the CUDA path through the C-ABI against the same vectors."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+import oracle_api as O
+from oracle_api import OracleAPI
+from pop_up_slam_b200 import graphgen as gg
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+G = json.load(open(os.path.join(HERE, "golden", "reference_build.json")))
+BUILDERS = {"build_interleaved": gg.build_interleaved, "build_bulk": gg.build_bulk}
+
+
+def _qdiff(a, b):
+    a, b = np.asarray(a), np.asarray(b)
+    s = np.sign(np.sum(a[..., 3:] * b[..., 3:], axis=-1))[..., None]
+    return max(np.abs(a[..., :3] - b[..., :3]).max(), np.abs(a[..., 3:] * s - b[..., 3:]).max())
+
+
+def test_oracle_reproduces_the_reference_factor_vectors():
+    worst = dict(err=0.0, jac=0.0, manifold=0.0)
+    n = 0
+    for c in G["factors"]:
+        if c["kind"] == "exmap":
+            worst["manifold"] = max(worst["manifold"], np.abs(O.pose_exmap(np.array(c["pose"]), np.array(c["d6"])) - c["pose_out"]).max(),
+                                    np.abs(O.plane_exmap(np.array(c["plane"]), np.array(c["d3"])) - c["plane_out"]).max(),
+                                    _qdiff(O.pose_oplus(np.array(c["pose"]), np.array(c["pose2"])), c["oplus"]),
+                                    _qdiff(O.pose_ominus(np.array(c["pose2"]), np.array(c["pose"])), c["ominus"]))
+            continue
+        api = OracleAPI()
+        if c["robust"]:
+            api.set_robust(1, c["b"])
+        if c["kind"] == "pose_plane":
+            f = api.add_pose_plane(api.add_pose(c["pose"]), api.add_plane(c["plane"]), c["meas"], c["sqrtinf"])
+        elif c["kind"] == "odometry":
+            f = api.add_odometry(api.add_pose(c["pose"]), api.add_pose(c["pose2"]), c["meas"], c["sqrtinf"])
+        elif c["kind"] == "pose_prior":
+            f = api.add_pose_prior(api.add_pose(c["pose"]), c["meas"], c["sqrtinf"])
+        else:
+            f = api.add_plane_prior(api.add_plane(c["plane"]), c["meas"], c["sqrtinf"])
+        e = api.factor_error(f)
+        J, _ = api.factor_jacobian(f, 0)
+        Jr = np.array(c["jacobian"])
+        worst["err"] = max(worst["err"], np.abs(e - c["error"]).max() / max(1.0, np.abs(e).max()))
+        worst["jac"] = max(worst["jac"], np.abs(J - Jr).max() / max(1.0, np.abs(Jr).max()))
+        n += 1
+    assert n >= 190
+    assert worst["err"] < 1e-12 and worst["jac"] < 1e-8 and worst["manifold"] < 1e-12, worst
+
+
+@pytest.mark.parametrize("name", ["config1_seed0", "config2_seed0", "config3_small_huber", "config3_full_20it"])
+def test_oracle_reproduces_the_reference_lm_runs(name):
+    """same iteration count, lambda / accept trace, chi2 and estimates as the reference's own optimiser (numeric-Jacobian
+    mode of the oracle = the reference's algorithm); config3_full_20it is the bench workload: its chi2 after the 20 capped
+    iterations, 256 841.33, is what bench.py prints as chi2_final_cpu_numeric_jacobians."""
+    r = G["runs"][name]
+    g = gg.make_config(r["config"], seed=r["seed"], **r["kw"])
+    api = OracleAPI()
+    api.set_jacobian_mode(0)
+    api.set_reuse_ordering(1)
+    ids = BUILDERS[r["builder"]](api, g)
+    gg.configure(api, g)
+    assert abs(api.chi2() - r["chi2_initial"]) <= 1e-11 * r["chi2_initial"]
+    assert api.batch_optimize() == r["iterations"]
+    tr = api.trace()
+    assert tr["accepted"].tolist() == r["accepted"]
+    assert np.allclose(tr["lam"], r["lambda_trace"], rtol=1e-12)
+    for a, b in zip(tr["chi2_new"], r["chi2_trace"]):
+        if b is not None:
+            assert abs(a - b) <= 1e-9 * b
+    assert abs(api.chi2() - r["chi2_final"]) <= 1e-10 * r["chi2_final"]
+    P, L = api.get_poses(ids["pose_ids"]), api.get_planes(ids["plane_ids"])
+    assert _qdiff(P[::r["stride"]], r["poses"]) < 1e-8
+    assert np.abs(L[::r["plane_stride"]] - np.array(r["planes"])).max() < 1e-8
+    starts = [api.node_start(int(i)) for i in list(ids["pose_ids"][:6]) + list(ids["plane_ids"][:6])]
+    assert starts == r["node_starts"]
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# GPU: the CUDA path against the reference-generated vectors
+# ------------------------------------------------------------------------------------------------------------------
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", ["config1_seed0", "config2_seed0"])
+def test_gpu_matches_the_reference_lm_runs(name):
+    """Well-conditioned graphs: the CUDA path (closed-form Jacobians, Schur + PCG) follows the reference's own optimiser
+    (eps = 1e-4 numerical Jacobians, CHOLMOD-style direct solve): same iterations and accept sequence, chi2 and estimates
+    within the 1e-4 bar of BASELINE.json (observed ~1e-6: the reference's Jacobian truncation error)."""
+    from pop_up_slam_b200.capi import GpuGraphAPI
+    r = G["runs"][name]
+    g = gg.make_config(r["config"], seed=r["seed"], **r["kw"])
+    gpu = GpuGraphAPI()
+    ids = BUILDERS[r["builder"]](gpu, g)
+    gg.configure(gpu, g)
+    assert abs(gpu.chi2() - r["chi2_initial"]) <= 1e-10 * r["chi2_initial"]
+    assert gpu.batch_optimize() == r["iterations"]
+    assert gpu.trace()["accepted"].tolist() == r["accepted"]
+    assert abs(gpu.chi2() - r["chi2_final"]) <= 1e-4 * r["chi2_final"]
+    P, L = gpu.get_poses(ids["pose_ids"]), gpu.get_planes(ids["plane_ids"])
+    assert _qdiff(P[::r["stride"]], r["poses"]) < 1e-4
+    sg = np.sign(np.sum(L[::r["plane_stride"]] * np.array(r["planes"]), axis=1))[:, None]
+    assert np.abs(L[::r["plane_stride"]] * sg - np.array(r["planes"])).max() < 1e-4
+    starts = [gpu.node_start(int(i)) for i in list(ids["pose_ids"][:6]) + list(ids["plane_ids"][:6])]
+    assert starts == r["node_starts"]
+
+
+@pytest.mark.gpu
+def test_gpu_objective_equals_the_reference_at_the_reference_estimate():
+    """Huber corridor with outliers: chi2 evaluated by the CUDA path AT the reference's final estimate equals the reference's
+    own chi2 (robustified residuals of every factor type: the objective functions are the same function), and the initial
+    chi2 agrees as well."""
+    from pop_up_slam_b200.capi import GpuGraphAPI
+    r = G["runs"]["config3_small_huber"]
+    g = gg.make_config(r["config"], seed=r["seed"], **r["kw"])
+    gpu = GpuGraphAPI()
+    ids = gg.build_bulk(gpu, g)
+    gg.configure(gpu, g)
+    assert abs(gpu.chi2() - r["chi2_initial"]) <= 1e-10 * r["chi2_initial"]
+    assert r["stride"] == 1 and r["plane_stride"] == 1
+    gpu.init_poses(ids["pose_ids"], np.array(r["poses"]))
+    gpu.init_planes(ids["plane_ids"], np.array(r["planes"]))
+    assert abs(gpu.chi2() - r["chi2_final"]) <= 1e-10 * r["chi2_final"]
