@@ -159,6 +159,12 @@ int pus_set_properties(pus_handle h, const pus_properties* in);
  * kind 0 none, 1 cost_huber(d,b), 2 cost_pseudo_huber(d,b); applied per residual component
  * (Factor.h:67-77). */
 int pus_set_robust(pus_handle h, int kind, double b);
+/* Properties::force_numerical_jacobian (ISAM/include/isam/Properties.h:44-45) / Factor::jacobian -> numericalDiff
+ * (Factor.h:126-139, ISAM/isamlib/numericalDiff.cpp:41-87).  numeric = 0 (default): closed-form Jacobian blocks;
+ * numeric = 1: the reference's own scheme on the device -- central differences, epsilon = 1e-4, through the exmaps, of the
+ * weighted robustified residual, linearisation point restored through the Euler round trip as upstream.  With it a solve
+ * follows the reference's trajectory (same accept / reject sequence) where its truncation error decides near-tie steps. */
+int pus_set_jacobian_mode(pus_handle h, int numeric);
 int pus_get_solver_options(pus_handle h, pus_solver_options* out);
 int pus_set_solver_options(pus_handle h, const pus_solver_options* in);
 

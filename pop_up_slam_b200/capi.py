@@ -340,6 +340,11 @@ class GpuGraphAPI(GraphAPI):
     def set_stream(self, cuda_stream_ptr):
         self._chk(self.lib.pus_set_stream(self.h, C.c_void_p(cuda_stream_ptr)))
 
+    def set_jacobian_mode(self, mode):
+        """Same convention as the oracle binding: 0 = the reference's numerical differences (numericalDiff, eps = 1e-4), 1 = closed
+        forms (the default of the CUDA library)."""
+        self._chk(self.lib.pus_set_jacobian_mode(self.h, 1 if int(mode) == 0 else 0))
+
     def get_solver_options(self):
         o = SolverOptions()
         self._chk(self.lib.pus_get_solver_options(self.h, C.byref(o)))

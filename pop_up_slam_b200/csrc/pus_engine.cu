@@ -48,6 +48,7 @@ struct Solver {
   pus_properties prop;
   int robust_kind = 0;
   double robust_b = 1.0;
+  int jac_numeric = 0;
   pus_solver_options opt;
   Compiled c;
   uint64_t compiled_topo = 0;
@@ -65,6 +66,12 @@ struct Solver {
   int step = 0;
   cudaStream_t stream = nullptr;
   bool own_stream = false;
+  cudaStream_t saved_stream = nullptr;   // this handle's own stream while it rides on a batch's stream (adopt_stream / release_stream)
+  bool saved_own = false, borrowing = false;
+  int borrow_depth = 0;
+  bool values_dirty = false;             // host values changed since the last upload (pus_init_*): device copies are stale
+  DevGraph* d_batch = nullptr;           // parameter blocks of a batched launch (grow-only)
+  int d_batch_cap = 0;
   std::map<std::string, std::pair<double*, size_t>> named;  // debug access to double buffers
   DevGraph hd;
   DevGraph* d_graph = nullptr;
@@ -273,13 +280,14 @@ static int upload(Solver* s) {
   s->stats.h2d_ms = ms;
   s->stats.h2d_bytes = bytes;
   s->uploaded = true;
+  s->values_dirty = false;
   return 0;
 }
 
 static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int debug_stage, double debug_lambda) {
   p.method = s->prop.method; p.eps2 = s->prop.epsilon2; p.eps_abs = s->prop.epsilon_abs; p.eps_rel = s->prop.epsilon_rel;
   p.max_iter = s->prop.max_iterations; p.lambda0 = s->prop.lm_lambda0; p.lambda_factor = s->prop.lm_lambda_factor;
-  p.robust_kind = s->robust_kind; p.robust_b = s->robust_b;
+  p.robust_kind = s->robust_kind; p.robust_b = s->robust_b; p.jac_numeric = s->jac_numeric;
   p.pcg_tol = s->opt.pcg_rel_tol; p.pcg_max_iter = s->opt.pcg_max_iter;
   p.prec_refresh = s->opt.reserved[0] == 1 ? 0 : 1;
   p.refresh_pct = s->opt.reserved[3] > 0 ? s->opt.reserved[3] : 200;   // rebuild when its > pct% of the post-build count + add
@@ -337,10 +345,14 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
     hg[i] = ss[i]->hd;
   }
   DevGraph* d_graphs = s0->d_graph;
-  DevGraph* d_tmp = nullptr;
   if (n > 1) {
-    CUDA_OK(cudaMalloc(&d_tmp, sizeof(DevGraph) * n));
-    d_graphs = d_tmp;
+    if (s0->d_batch_cap < n) {
+      if (s0->d_batch) cudaFree(s0->d_batch);
+      s0->d_batch = nullptr; s0->d_batch_cap = 0;
+      CUDA_OK(cudaMalloc(&s0->d_batch, sizeof(DevGraph) * (size_t)n));
+      s0->d_batch_cap = n;
+    }
+    d_graphs = s0->d_batch;
   }
   CUDA_OK(cudaMemcpyAsync(d_graphs, hg.data(), sizeof(DevGraph) * n, cudaMemcpyHostToDevice, s0->stream));
   CUDA_OK(cudaMemsetAsync(s0->d_bar, 0, 32 * 1024 * sizeof(unsigned), s0->stream));
@@ -353,10 +365,9 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
   for (int i = 0; i < n; i++) spanning = spanning || (hg[i].span_w > 1);
   void* kfn = spanning ? span_kernel_ptr() : (void*)kplain::lm_kernel;
   cudaError_t le = cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kThreads), args, kSmemBytes, s0->stream);
-  if (le != cudaSuccess) { g_err = std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(le); if (d_tmp) cudaFree(d_tmp); return -1; }
+  if (le != cudaSuccess) { g_err = std::string("cudaLaunchCooperativeKernel: ") + cudaGetErrorString(le); return -1; }
   CUDA_OK(cudaEventRecord(s0->ev1, s0->stream));
   cudaError_t se = cudaEventSynchronize(s0->ev1);
-  if (d_tmp) cudaFree(d_tmp);
   if (se != cudaSuccess) { g_err = std::string("lm_kernel: ") + cudaGetErrorString(se); return -1; }
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, s0->ev0, s0->ev1));
@@ -409,12 +420,25 @@ static int download(Solver** ss, int n) {
 }
 
 // a batch rides on the first handle's stream: the others drop their own stream (if any) and borrow it
+// (for the duration of the batched call only: release_stream() gives every handle its own stream back, so a later
+// pus_destroy of the first handle cannot leave the others with a dangling cudaStream_t)
 static void adopt_stream(Solver* s, cudaStream_t st) {
-  if (s->stream == st) { return; }
-  if (s->own_stream && s->stream) cudaStreamDestroy(s->stream);
+  s->borrow_depth++;
+  if (s->borrowing) { s->stream = st; return; }
+  s->saved_stream = s->stream; s->saved_own = s->own_stream; s->borrowing = true;
   s->own_stream = false;
   s->stream = st;
 }
+static void release_stream(Solver* s) {
+  if (!s->borrowing || --s->borrow_depth > 0) return;
+  s->stream = s->saved_stream; s->own_stream = s->saved_own; s->borrowing = false;
+  s->saved_stream = nullptr; s->saved_own = false;
+}
+struct BatchStreams {   // RAII: handles 1..n-1 ride on handle 0's stream until the call returns
+  pus_handle* hs; int n;
+  BatchStreams(pus_handle* h, int k, cudaStream_t st) : hs(h), n(k) { for (int i = 1; i < n; i++) adopt_stream(reinterpret_cast<Solver*>(hs[i]), st); }
+  ~BatchStreams() { for (int i = 1; i < n; i++) release_stream(reinterpret_cast<Solver*>(hs[i])); }
+};
 
 }  // namespace pus
 
@@ -476,6 +500,7 @@ int pus_destroy(pus_handle h) {
   cudaSetDevice(s->device);
   for (void* pp : s->span_peers) if (pp) cudaIpcCloseMemHandle(pp);
   s->free_device();
+  if (s->d_batch) cudaFree(s->d_batch);
   if (s->scratch) cudaFree(s->scratch);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -509,12 +534,12 @@ int pus_add_planes(pus_handle h, int n, const double* v, int* out) {
 int pus_init_pose(pus_handle h, int id, const double* v) {
   NEED(h);
   if (!SV(h)->g.ok_node(id, NODE_POSE)) { g_err = "bad pose id"; return -1; }
-  SV(h)->g.init_node(id, v); return 0;
+  SV(h)->g.init_node(id, v); SV(h)->values_dirty = true; return 0;
 }
 int pus_init_plane(pus_handle h, int id, const double* v) {
   NEED(h);
   if (!SV(h)->g.ok_node(id, NODE_PLANE)) { g_err = "bad plane id"; return -1; }
-  SV(h)->g.init_node(id, v); return 0;
+  SV(h)->g.init_node(id, v); SV(h)->values_dirty = true; return 0;
 }
 int pus_init_poses(pus_handle h, int n, const int* ids, const double* v) {
   for (int i = 0; i < n; i++) if (pus_init_pose(h, ids[i], v + 7 * i) < 0) return -1;
@@ -628,15 +653,15 @@ int pus_set_robust(pus_handle h, int kind, double b) {
   if (kind < 0 || kind > 2 || !(b > 0)) { g_err = "bad robust cost"; return -1; }
   SV(h)->robust_kind = kind; SV(h)->robust_b = b; return 0;
 }
+int pus_set_jacobian_mode(pus_handle h, int numeric) { NEED(h); SV(h)->jac_numeric = numeric ? 1 : 0; return 0; }
 int pus_get_solver_options(pus_handle h, pus_solver_options* out) { NEED(h); *out = SV(h)->opt; return 0; }
 int pus_set_solver_options(pus_handle h, const pus_solver_options* in) { NEED(h); SV(h)->opt = *in; return 0; }
 
 int pus_upload(pus_handle h) { NEED(h); return upload(SV(h)); }
 int pus_upload_many(pus_handle* hs, int n) {
-  if (n > 1) {
-    if (ensure_device(SV(hs[0])) < 0) return -1;
-    for (int i = 1; i < n; i++) adopt_stream(SV(hs[i]), SV(hs[0])->stream);
-  }
+  if (n <= 0) return 0;
+  if (ensure_device(SV(hs[0])) < 0) return -1;
+  BatchStreams bs(hs, n, SV(hs[0])->stream);
   for (int i = 0; i < n; i++) if (upload(SV(hs[i])) < 0) return -1;
   return 0;
 }
@@ -644,10 +669,8 @@ static int solve_many(pus_handle* hs, int n, int* iters, int mode, int restore) 
   if (n <= 0) return 0;
   std::vector<Solver*> ss(n);
   for (int i = 0; i < n; i++) ss[i] = SV(hs[i]);
-  if (n > 1) {
-    if (ensure_device(ss[0]) < 0) return -1;
-    for (int i = 1; i < n; i++) adopt_stream(ss[i], ss[0]->stream);
-  }
+  if (ensure_device(ss[0]) < 0) return -1;
+  BatchStreams bs(hs, n, ss[0]->stream);
   if (launch(ss.data(), n, mode, restore, 0, 0.0) < 0) return -1;
   if (iters) for (int i = 0; i < n; i++) iters[i] = ss[i]->res.iterations;
   return 0;
@@ -662,9 +685,12 @@ int pus_solve_resident_many(pus_handle* hs, int n, int* iters) {
 }
 int pus_download(pus_handle h) { NEED(h); Solver* s = SV(h); return download(&s, 1); }
 int pus_download_many(pus_handle* hs, int n) {
+  if (n <= 0) return 0;
   std::vector<Solver*> ss(n);
   for (int i = 0; i < n; i++) ss[i] = SV(hs[i]);
-  return n ? download(ss.data(), n) : 0;
+  if (ensure_device(ss[0]) < 0) return -1;
+  BatchStreams bs(hs, n, ss[0]->stream);
+  return download(ss.data(), n);
 }
 
 int pus_batch_optimize(pus_handle h, int* iters) {
@@ -678,7 +704,7 @@ int pus_batch_optimize_many(pus_handle* hs, int n, int* iters) {
   if (n <= 0) return 0;
   Solver* s0 = SV(hs[0]);
   if (ensure_device(s0) < 0) return -1;
-  for (int i = 1; i < n; i++) adopt_stream(SV(hs[i]), s0->stream);
+  BatchStreams bs(hs, n, s0->stream);
   if (pus_upload_many(hs, n) < 0) return -1;
   if (solve_many(hs, n, iters, MODE_BATCH, 0) < 0) return -1;
   return pus_download_many(hs, n);
@@ -745,7 +771,7 @@ int pus_span_emulate_optimize(pus_handle* hs, int world, int* iters) {
   if (world < 1 || world > 8) { g_err = "pus_span_emulate_optimize: world must be 1..8"; return -1; }
   Solver* s0 = SV(hs[0]);
   if (ensure_device(s0) < 0) return -1;
-  for (int i = 1; i < world; i++) adopt_stream(SV(hs[i]), s0->stream);
+  BatchStreams bs(hs, world, s0->stream);
   if (pus_upload_many(hs, world) < 0) return -1;
   std::vector<char*> arenas(world);
   for (int i = 0; i < world; i++) arenas[i] = reinterpret_cast<char*>(SV(hs[i])->arena);
@@ -810,7 +836,8 @@ int pus_refresh_plane_measurements(pus_handle h, int n_frames, const int* frame_
   NEED(h);
   Solver* s = SV(h);
   if (n_frames <= 0) return 0;
-  if (!s->uploaded || s->compiled_topo != s->g.topo_version) {
+  // (re-upload when the topology OR the host values changed: update_plane_measurement uses pose_vertex->value())
+  if (!s->uploaded || s->compiled_topo != s->g.topo_version || s->values_dirty) {
     if (upload(s) < 0) return -1;
   } else if (ensure_device(s) < 0) {
     return -1;
@@ -876,7 +903,7 @@ int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point,
   NEED(h);
   Solver* s = SV(h);
   if (n_points <= 0) return 0;
-  if (!s->uploaded || s->compiled_topo != s->g.topo_version) {
+  if (!s->uploaded || s->compiled_topo != s->g.topo_version || s->values_dirty) {
     if (upload(s) < 0) return -1;
   } else if (ensure_device(s) < 0) {
     return -1;

@@ -46,6 +46,7 @@ struct LmParams {
   int fine_timers;   // 1: sub-phase timers (perturbs the run slightly)
   int refresh_pct, refresh_add;  // lazy preconditioner refresh threshold
   int tma_mode;      // 0: TMA-staged W/Wt tiles when a warp owns several tiles (large graphs), 1: always, 2: never
+  int jac_numeric;   // 1: reference-Jacobian mode (central differences, numericalDiff.cpp:41-87) instead of the closed forms
 };
 
 struct LmResult {
@@ -156,7 +157,8 @@ __device__ __forceinline__ void team_barrier(Ctx& c) {
       for (int w = 0; w < c.span_w; w++)
         atomicAdd_system(reinterpret_cast<unsigned*>(reinterpret_cast<char*>(c.gbar) + c.peer_delta[w]), 1u);
       const unsigned long long t0 = gtime();
-      while (ld_acquire_sys_u32(c.gbar) < c.gbar_target) {
+      // (wrap-safe: the counters persist across launches and may pass 2^32 after many spanning solves)
+      while ((int)(ld_acquire_sys_u32(c.gbar) - c.gbar_target) < 0) {
         if (gtime() - t0 > 20000000000ull) __trap();   // a peer never arrived (20 s): fail instead of hanging the GPU
       }
       __threadfence_system();
@@ -170,7 +172,7 @@ __device__ __forceinline__ void team_barrier(Ctx& c) {
       c.bar_target += (unsigned)c.tsize;
       __threadfence();
       atomicAdd(c.bar, 1u);
-      while (ld_acquire_u32(c.bar) < c.bar_target) { }
+      while ((int)(ld_acquire_u32(c.bar) - c.bar_target) < 0) { }
       __threadfence();
     }
     __syncthreads();
@@ -505,6 +507,15 @@ __device__ __forceinline__ double* gj_invert_smem(double* Mc, double* Mn, double
 
 // Pose3d_Plane3d_Factor2 edges are rare (disabled in the shipped demo): keep their extra arithmetic out of the
 // register allocation of the common path
+// reference-Jacobian mode (pus_math.cuh: pose_plane_numeric / pose_factor_numeric): rarely used, kept out of line
+__device__ __noinline__ void pose_plane_numeric_dev(const double* pose, const double* plane, const double* meas, const double* sinf,
+                                                    int robust_kind, double robust_b, double* r, double* Jp, double* Jl, const double* rays) {
+  pose_plane_numeric(pose, plane, meas, sinf, robust_kind, robust_b, r, Jp, Jl, rays);
+}
+__device__ __noinline__ void pose_factor_numeric_dev(const double* p1, const double* p2, const double* meas, const double* sinf,
+                                                     int robust_kind, double robust_b, double* r, double* J1, double* J2) {
+  pose_factor_numeric(p1, p2, meas, sinf, robust_kind, robust_b, r, J1, J2);
+}
 __device__ __noinline__ void pose_plane2_linearize(const double* pose, const double* plane, const double* rays, const double* sinf,
                                                    int robust_kind, double robust_b, double* r, double* Jp, double* Jl) {
   const double unit[4] = {1, 0, 0, 0};
@@ -543,7 +554,10 @@ struct Phase {
         for (int i = 0; i < 4; i++) m[i] = G.pp_meas[(size_t)e * 4 + i];
         for (int i = 0; i < 6; i++) si[i] = G.pp_sinf[(size_t)e * 6 + i];
         double r[3], Jp[18], Jl[9];
-        if (G.n_f2 > 0 && G.pp_kind[e])   // Factor2: measurement re-popped from the edge's rays (kept out of line)
+        if (G.prm.jac_numeric)             // reference-Jacobian mode
+          pose_plane_numeric_dev(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, Jp, Jl,
+                                 (G.n_f2 > 0 && G.pp_kind[e]) ? G.pp_rays + (size_t)e * 6 : nullptr);
+        else if (G.n_f2 > 0 && G.pp_kind[e])   // Factor2: measurement re-popped from the edge's rays (kept out of line)
           pose_plane2_linearize(pose, pl, G.pp_rays + (size_t)e * 6, si, G.prm.robust_kind, G.prm.robust_b, r, Jp, Jl);
         else
           pose_plane_linearize(pose, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, Jp, Jl);
@@ -580,7 +594,8 @@ struct Phase {
       for (int t = 0; t < 21; t++) si[t] = G.pf_sinf[(size_t)f * 21 + t];
       double r[6], J1[36], J2[36];
       for (int t = 0; t < 36; t++) J2[t] = 0;
-      pose_factor_linearize(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
+      if (G.prm.jac_numeric) pose_factor_numeric_dev(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
+      else pose_factor_linearize(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
       double* o = G.PF + (size_t)f * 120;
       for (int a = 0; a < 6; a++)
         for (int b = 0; b < 6; b++) {
@@ -605,7 +620,8 @@ struct Phase {
       for (int t = 0; t < 4; t++) m[t] = G.lp_meas[(size_t)f * 4 + t];
       for (int t = 0; t < 6; t++) si[t] = G.lp_sinf[(size_t)f * 6 + t];
       double r[3], Jl[9];
-      pose_plane_linearize(nullptr, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, Jl);
+      if (G.prm.jac_numeric) pose_plane_numeric_dev(nullptr, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, Jl, nullptr);
+      else pose_plane_linearize(nullptr, pl, m, si, G.prm.robust_kind, G.prm.robust_b, r, nullptr, Jl);
       double* o = G.LP + (size_t)f * 12;
       for (int a = 0; a < 3; a++) {
         for (int b = 0; b < 3; b++) o[a * 3 + b] = Jl[a] * Jl[b] + Jl[3 + a] * Jl[3 + b] + Jl[6 + a] * Jl[6 + b];
@@ -856,31 +872,39 @@ struct Phase {
             }
           }
           __syncthreads();
+          // Members of a group are in pose-major slot order, so the observations one pose makes of this plane are
+          // contiguous.  Every (pose, pose) entry is owned by the thread of the FIRST member pair that maps to it, which
+          // sums the contributions of all duplicate pairs in a fixed order: no atomics, bit-reproducible.
           const int total = m * m * 36;
           for (int idx = tid; idx < total; idx += kThreads) {
             int mi = idx / (36 * m), rem = idx % (36 * m);
             int mj = rem / 36, en = rem % 36, a = en / 6, b = en % 6;
-            int ei = G.grp_mem[m0 + mi], ej = G.grp_mem[m0 + mj];
-            int pi = G.pp_pose[ei] - p0, pj = G.pp_pose[ej] - p0;
-            double v;
-            if (staged) {
-              v = Yg[mi * 18 + a * 3] * Wg[mj * 18 + b * 3] + Yg[mi * 18 + a * 3 + 1] * Wg[mj * 18 + b * 3 + 1] +
-                  Yg[mi * 18 + a * 3 + 2] * Wg[mj * 18 + b * 3 + 2];
-            } else {
-              double wi[3], wj[3];
-              for (int t = 0; t < 3; t++) {
-                wi[t] = ldc(G.W + (size_t)(ei >> 5) * kWStride + (a * 3 + t) * 32 + (ei & 31));
-                wj[t] = ldc(G.W + (size_t)(ej >> 5) * kWStride + (b * 3 + t) * 32 + (ej & 31));
+            const int ppi = G.pp_pose[G.grp_mem[m0 + mi]], ppj = G.pp_pose[G.grp_mem[m0 + mj]];
+            if ((mi > 0 && G.pp_pose[G.grp_mem[m0 + mi - 1]] == ppi) || (mj > 0 && G.pp_pose[G.grp_mem[m0 + mj - 1]] == ppj)) continue;
+            const int pi = ppi - p0, pj = ppj - p0;
+            double acc = 0;
+            for (int ui = mi; ui < m && G.pp_pose[G.grp_mem[m0 + ui]] == ppi; ui++)
+              for (int uj = mj; uj < m && G.pp_pose[G.grp_mem[m0 + uj]] == ppj; uj++) {
+                double v;
+                if (staged) {
+                  v = Yg[ui * 18 + a * 3] * Wg[uj * 18 + b * 3] + Yg[ui * 18 + a * 3 + 1] * Wg[uj * 18 + b * 3 + 1] +
+                      Yg[ui * 18 + a * 3 + 2] * Wg[uj * 18 + b * 3 + 2];
+                } else {
+                  const int ei = G.grp_mem[m0 + ui], ej = G.grp_mem[m0 + uj];
+                  double wi[3], wj[3];
+                  for (int t = 0; t < 3; t++) {
+                    wi[t] = ldc(G.W + (size_t)(ei >> 5) * kWStride + (a * 3 + t) * 32 + (ei & 31));
+                    wj[t] = ldc(G.W + (size_t)(ej >> 5) * kWStride + (b * 3 + t) * 32 + (ej & 31));
+                  }
+                  v = 0;
+                  for (int t = 0; t < 3; t++) {
+                    double y = wi[0] * His[0 * 3 + t] + wi[1] * His[1 * 3 + t] + wi[2] * His[2 * 3 + t];
+                    v += y * wj[t];
+                  }
+                }
+                acc += v;
               }
-              v = 0;
-              for (int t = 0; t < 3; t++) {
-                double y = wi[0] * His[0 * 3 + t] + wi[1] * His[1 * 3 + t] + wi[2] * His[2 * 3 + t];
-                v += y * wj[t];
-              }
-            }
-            // distinct (mi,mj) pairs of one group hit distinct entries unless a pose observes the
-            // plane twice; the atomic keeps that (rare) case correct
-            atomicAdd(&S0[(pi * 6 + a) * LD + pj * 6 + b], -v);
+            S0[(pi * 6 + a) * LD + pj * 6 + b] -= acc;
           }
         }
       }

@@ -495,6 +495,75 @@ PUS_HD void pose_factor_linearize(const double* p1, const double* p2, const doub
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Reference-Jacobian mode: the blocks the reference itself forms, by central differences through the exmaps
+// (ISAM/isamlib/numericalDiff.cpp:41-87, SYMMETRIC, epsilon = 1e-4; Factor::jacobian Factor.h:126-139).  The product
+// defaults to the closed forms above; this mode exists so that a solve can follow the reference's own trajectory
+// (its Jacobians carry an O(eps^2) truncation error that decides near-tie accept / reject steps).
+// As upstream, the perturbed point is restored through update0(vector0()): a pose is rebuilt from its wrapped Euler
+// angles (Pose3d::set, Pose3d.h:152-155), a plane re-normalised (Plane3d::set, isam_plane3d.h:139-142); every column is
+// (f(x (+) eps e_j) - f(x (+) -eps e_j)) / (eps + eps) of the weighted, robustified residual.
+// ---------------------------------------------------------------------------------------------------------------------
+PUS_HD void pose_euler_roundtrip(const double* p, double* out) {
+  double yaw, pitch, roll;
+  quat_to_euler(p + 3, yaw, pitch, roll);
+  out[0] = p[0]; out[1] = p[1]; out[2] = p[2];
+  euler_to_quat(standard_rad(yaw), standard_rad(pitch), standard_rad(roll), out + 3);
+}
+
+PUS_HD void pose_plane_numeric(const double* pose, const double* plane, const double* meas, const double* sinf, int robust_kind,
+                               double robust_b, double* r, double* Jp, double* Jl, const double* rays = nullptr) {
+  const double eps = 0.0001;
+  double p0[7], l0[4] = {plane[0], plane[1], plane[2], plane[3]};
+  normalize4(l0);
+  if (pose) {
+    pose_euler_roundtrip(pose, p0);
+    for (int j = 0; j < 6; j++) {
+      double d[6] = {0, 0, 0, 0, 0, 0}, pp[7], yp[3], ym[3];
+      d[j] = eps;
+      pose_exmap(p0, d, pp);
+      pose_plane_linearize(pp, l0, meas, sinf, robust_kind, robust_b, yp, nullptr, nullptr, rays);
+      d[j] = -eps;
+      pose_exmap(p0, d, pp);
+      pose_plane_linearize(pp, l0, meas, sinf, robust_kind, robust_b, ym, nullptr, nullptr, rays);
+      for (int i = 0; i < 3; i++) Jp[i * 6 + j] = (yp[i] - ym[i]) / (eps + eps);
+    }
+  }
+  for (int j = 0; j < 3; j++) {
+    double d[3] = {0, 0, 0}, lp[4], yp[3], ym[3];
+    d[j] = eps;
+    plane_exmap(l0, d, lp);
+    pose_plane_linearize(pose ? p0 : nullptr, lp, meas, sinf, robust_kind, robust_b, yp, nullptr, nullptr, rays);
+    d[j] = -eps;
+    plane_exmap(l0, d, lp);
+    pose_plane_linearize(pose ? p0 : nullptr, lp, meas, sinf, robust_kind, robust_b, ym, nullptr, nullptr, rays);
+    for (int i = 0; i < 3; i++) Jl[i * 3 + j] = (yp[i] - ym[i]) / (eps + eps);
+  }
+  pose_plane_linearize(pose ? p0 : nullptr, l0, meas, sinf, robust_kind, robust_b, r, nullptr, nullptr, rays);
+}
+
+PUS_HD void pose_factor_numeric(const double* p1, const double* p2, const double* meas, const double* sinf, int robust_kind,
+                                double robust_b, double* r, double* J1, double* J2) {
+  const double eps = 0.0001;
+  double a0[7], b0[7];
+  pose_euler_roundtrip(p1, a0);
+  if (p2) pose_euler_roundtrip(p2, b0);
+  for (int k = 0; k < (p2 ? 2 : 1); k++) {
+    double* J = k ? J2 : J1;
+    for (int j = 0; j < 6; j++) {
+      double d[6] = {0, 0, 0, 0, 0, 0}, pp[7], yp[6], ym[6];
+      d[j] = eps;
+      pose_exmap(k ? b0 : a0, d, pp);
+      pose_factor_linearize(k ? a0 : pp, p2 ? (k ? pp : b0) : nullptr, meas, sinf, robust_kind, robust_b, yp, nullptr, nullptr);
+      d[j] = -eps;
+      pose_exmap(k ? b0 : a0, d, pp);
+      pose_factor_linearize(k ? a0 : pp, p2 ? (k ? pp : b0) : nullptr, meas, sinf, robust_kind, robust_b, ym, nullptr, nullptr);
+      for (int i = 0; i < 6; i++) J[i * 6 + j] = (yp[i] - ym[i]) / (eps + eps);
+    }
+  }
+  pose_factor_linearize(a0, p2 ? b0 : nullptr, meas, sinf, robust_kind, robust_b, r, nullptr, nullptr);
+}
+
 // inverse of a symmetric positive definite 3x3 given as full row-major 9; out full 9
 PUS_HD void sym3_inverse(const double* A, double* Ai) {
   double a = A[0], b = A[1], c = A[2], d = A[4], e = A[5], f = A[8];

@@ -28,6 +28,14 @@ void hm_pose_factor_residual(const double* p1, const double* p2, const double* m
                              double* r) {
   pose_factor_linearize(p1, p2, meas, sinf, rk, rb, r, nullptr, nullptr);
 }
+void hm_pose_plane_numeric(const double* pose, const double* plane, const double* meas, const double* sinf, int rk,
+                           double rb, double* r, double* Jp, double* Jl) {
+  pose_plane_numeric(pose, plane, meas, sinf, rk, rb, r, Jp, Jl);
+}
+void hm_pose_factor_numeric(const double* p1, const double* p2, const double* meas, const double* sinf, int rk, double rb,
+                            double* r, double* J1, double* J2) {
+  pose_factor_numeric(p1, p2, meas, sinf, rk, rb, r, J1, J2);
+}
 void hm_pose_exmap(const double* p, const double* d, double* out) { pose_exmap(p, d, out); }
 void hm_plane_exmap(const double* p, const double* d, double* out) { plane_exmap(p, d, out); }
 void hm_pose_oplus(const double* a, const double* b, double* out) { pose_oplus(a, b, out); }

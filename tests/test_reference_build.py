@@ -134,6 +134,8 @@ def hm():
     P = C.POINTER(C.c_double)
     lib.hm_pose_plane_linearize.argtypes = [P, P, P, P, C.c_int, C.c_double, P, P, P]
     lib.hm_pose_factor_linearize.argtypes = [P, P, P, P, C.c_int, C.c_double, P, P, P]
+    lib.hm_pose_plane_numeric.argtypes = [P, P, P, P, C.c_int, C.c_double, P, P, P]
+    lib.hm_pose_factor_numeric.argtypes = [P, P, P, P, C.c_int, C.c_double, P, P, P]
     return lib
 
 
@@ -174,6 +176,49 @@ def test_product_math_header_matches_the_reference(hm, robust):
         worst_j = max(worst_j, np.abs(J - Jr).max() / max(1.0, np.abs(Jr).max()))
     assert worst_r < 1e-12, worst_r
     assert worst_j < (2e-2 if robust else 2e-5), worst_j
+
+
+@pytest.mark.parametrize("robust", [0, 1])
+def test_product_reference_jacobian_mode_matches_numericaldiff(hm, robust):
+    """pus_set_jacobian_mode(h, 1): pose_plane_numeric / pose_factor_numeric of pus_math.cuh (what the kernels run in that
+    mode) reproduce the reference's numericalDiff blocks (numericalDiff.cpp:41-87) to the rounding of the differences."""
+    rng = np.random.default_rng(12)
+    ref = R.RefAPI()
+    if robust:
+        ref.set_robust(1, 0.8)
+    n = 100
+    poses = [rand_pose(rng) for _ in range(n)]
+    planes = [rand_plane(rng) for _ in range(n)]
+    pid, lid = ref.add_poses(np.array(poses)), ref.add_planes(np.array(planes))
+    worst_r = worst_j = 0.0
+    for i in range(n):
+        meas = O.plane_exmap(O.plane_transform(O.pose_wTo(poses[i]), planes[i]), rng.normal(0, 0.3, 3))
+        si = ut(rng, 3)
+        f = ref.add_pose_plane(pid[i], lid[i], meas, si)
+        Jr, rr = ref.factor_jacobian(f)
+        r, Jp, Jl = np.zeros(3), np.zeros(18), np.zeros(9)
+        hm.hm_pose_plane_numeric(_dp(poses[i]), _dp(planes[i]), _dp(np.ascontiguousarray(meas)), _dp(si), robust, 0.8, _dp(r), _dp(Jp), _dp(Jl))
+        J = np.hstack([Jp.reshape(3, 6), Jl.reshape(3, 3)])
+        worst_r = max(worst_r, np.abs(r - rr).max() / max(1.0, np.abs(rr).max()))
+        worst_j = max(worst_j, np.abs(J - Jr).max() / max(1.0, np.abs(Jr).max()))
+        j = (i + 1) % n
+        m = O.pose_vector(O.pose_ominus(poses[j], poses[i])) + rng.normal(0, 0.05, 6)
+        si6 = ut(rng, 6)
+        f = ref.add_odometry(pid[i], pid[j], m, si6)
+        Jr, rr = ref.factor_jacobian(f)
+        r6, J1, J2 = np.zeros(6), np.zeros(36), np.zeros(36)
+        hm.hm_pose_factor_numeric(_dp(poses[i]), _dp(poses[j]), _dp(np.ascontiguousarray(m)), _dp(si6), robust, 0.8, _dp(r6), _dp(J1), _dp(J2))
+        J = np.hstack([J1.reshape(6, 6), J2.reshape(6, 6)])
+        worst_r = max(worst_r, np.abs(r6 - rr).max() / max(1.0, np.abs(rr).max()))
+        worst_j = max(worst_j, np.abs(J - Jr).max() / max(1.0, np.abs(Jr).max()))
+        f = ref.add_pose_prior(pid[i], O.pose_vector(poses[i]) + rng.normal(0, 0.05, 6), si6)
+        Jr, rr = ref.factor_jacobian(f)
+        mm = ref.get_measurement(f, 6)
+        hm.hm_pose_factor_numeric(_dp(poses[i]), None, _dp(np.ascontiguousarray(mm)), _dp(si6), robust, 0.8, _dp(r6), _dp(J1), _dp(J2))
+        worst_r = max(worst_r, np.abs(r6 - rr).max() / max(1.0, np.abs(rr).max()))
+        worst_j = max(worst_j, np.abs(J1.reshape(6, 6) - Jr).max() / max(1.0, np.abs(Jr).max()))
+    assert worst_r < 1e-12, worst_r
+    assert worst_j < 1e-8, worst_j
 
 
 def _solve_both(g, builder, jac_mode=0, **props):
