@@ -61,7 +61,8 @@ typedef struct pus_solver_options {
                         *   [0] = 1  rebuild the preconditioner for every linear solve (no lazy refresh)
                         *   [1] = 1  no PCG warm start after a rejected LM step
                         *   [2]      bit 0: sub-phase timers in pus_stats.phase_ms[13..23]; bit 1: always stage W / Wt
-                        *            tiles by bulk async copy (the large-graph data path); bit 2: never
+                        *            tiles by bulk async copy (the large-graph data path); bit 2: never; bit 3: force the
+                        *            three-level preconditioner (default: graphs > 5120 poses); bit 4: force two levels
                         *   [3] > 0  lazy-refresh threshold in percent of the post-build iteration count (default 200) */
 } pus_solver_options;
 

@@ -15,6 +15,7 @@ __device__ void linearize(Phase& ph, Ctx& c) {
 // Schur complement set-up for a damping value.  Hll^-1 (part of the operator) is always rebuilt; the two-level
 // preconditioner (dense diagonal blocks + coarse Galerkin inverse) only when `rebuild` -- a stale
 // preconditioner changes the PCG iteration count, never the solution.  Returns the buffer index of A_c^-1.
+__device__ __forceinline__ bool G_levels3(const Phase& ph) { return ph.G.levels == 3; }
 __device__ int schur_setup(Phase& ph, Ctx& c, double lambda, Timer& ft, bool rebuild, int acinv_prev) {
   ft.sync();
   ph.plane_inverse(lambda);
@@ -27,6 +28,7 @@ __device__ int schur_setup(Phase& ph, Ctx& c, double lambda, Timer& ft, bool reb
   team_barrier(c);
   ft.lap(10);
   ph.coarse_assemble(lambda);
+  if (G_levels3(ph)) ph.build_groups(lambda);   // level 2: needs Wc2 / Yc2 (behind the barrier above) only
   team_barrier(c);
   ft.lap(11);
   int r = ph.coarse_invert();
@@ -136,6 +138,7 @@ __device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
   c.gbar = G.gbar;
   c.use_tma = (P.tma_mode == 1) || (P.tma_mode == 0 && G.ntile_pl > 2 * c.tsize * kWarps);
   c.smem_cache_ok = 0;
+  c.l3_local = (G.levels == 3 && 6 * G.nc <= kL3Local) ? 1 : 0;
   if (P.restore_init) { ph.restore_init(); team_barrier(c); }
   if (P.mode == MODE_CHI2) {
     double e = ph.chi2(false);

@@ -178,6 +178,10 @@ static int upload(Solver* s) {
   cudaEvent_t e0 = s->ev0, e1 = s->ev1;
   long long bytes = 0;
   CUDA_OK(cudaEventRecord(e0, s->stream));
+  {   // preconditioner levels: by graph size, or forced through pus_solver_options.reserved[2] (bit 3: three, bit 4: two)
+    const int want = (s->opt.reserved[2] & 8) ? 3 : ((s->opt.reserved[2] & 16) ? 2 : 0);
+    if (want != s->g.force_levels) { s->g.force_levels = want; s->g.topo_version++; }
+  }
   const bool rebuild = (s->compiled_topo != s->g.topo_version) || !s->uploaded;
   if (rebuild) {
     s->recycle_device();
@@ -202,6 +206,8 @@ static int upload(Solver* s) {
     UP(ce_ptr); UP(ce_node); UP(ce_plane); UP(ce_lo); UP(ce_hi); UP(n2ce_ptr); UP(n2ce);
     UP(hv_plane); UP(lp_ptr); UP(lp_cea); UP(lp_ceb); UP(fp_ptr); UP(fp_f);
     d.n_hv = c.n_hv;
+    UP(ce2_node); UP(ce2_plane); UP(ce2_lo); UP(ce2_hi); UP(g2_ptr); UP(g2_ce);
+    d.levels = c.levels; d.nc2 = c.nc2; d.nce2 = c.nce2; d.ng2 = c.ng2;
 #undef UP
     const size_t N = c.N, M = c.M, E = c.nslot, T = c.ntile, TL = c.ntile_pl;
 #define AL(field, n, name) if (s->dalloc(&d.field, (size_t)(n), name) < 0) return -1
@@ -213,6 +219,7 @@ static int upload(Solver* s) {
     AL(ypart, 8, "ypart");
     AL(Binv, (size_t)c.nblk * kBlockDim * kBlockDim, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc"); AL(Yc, (size_t)c.nce * 18, "Yc");
     AL(Ac[0], ac_doubles(6 * c.nc_pad), "Ac0"); AL(Ac[1], ac_doubles(6 * c.nc_pad), "Ac1");
+    AL(Wc2, (size_t)c.nce2 * 18, "Wc2"); AL(Yc2, (size_t)c.nce2 * 18, "Yc2"); AL(D2inv, (size_t)c.ng2 * kBlockDim * kBlockDim, "D2inv");
 #undef AL
     {
       // The vectors the PCG phases exchange live in ONE allocation (the "mirror arena"): when one graph spans several
@@ -222,6 +229,7 @@ static int upload(Solver* s) {
           {&d.vl, M * 3, "vl"}, {&d.dl, M * 3, "dl"}, {&d.upart, (size_t)c.n_upart * 3, "upart"},
           {&d.x, N * 6, "x"}, {&d.r, N * 6, "r"}, {&d.z, N * 6, "z"}, {&d.q, N * 6, "q"}, {&d.b, N * 6, "b"},
           {&d.pv[0], N * 6, "pv0"}, {&d.pv[1], N * 6, "pv1"}, {&d.xprev, N * 6, "xprev"}, {&d.zc, (size_t)6 * c.nc, "zc"},
+          {&d.zc2, (size_t)6 * c.nc2, "zc2"},
           {&d.rcpart[0], (size_t)c.nblk * 12, "rcpart0"}, {&d.rcpart[1], (size_t)c.nblk * 12, "rcpart1"},
           {&d.qcpart, (size_t)c.nblk * 12, "qcpart"}, {&d.red, (size_t)4 * 4 * 2048, "red"}};
       size_t total = 32;   // first 256 bytes: the cross-rank barrier counter and its persisted target
@@ -1095,7 +1103,8 @@ long long pus_debug_fetch(pus_handle h, const char* name, double* out, long long
     double d[12] = {(double)c.N, (double)c.M, (double)c.Epl, (double)c.Epf, (double)c.Elp, (double)c.ntile, (double)c.nblk, (double)c.nc, (double)c.nce, (double)c.ngrp, (double)c.nslot, (double)c.ntile_pl};
     if (cap >= 12) std::memcpy(out, d, sizeof(d));
     if (cap >= 14) { out[12] = c.SP; out[13] = c.nc_pad; }
-    return 12;
+    if (cap >= 18) { out[14] = c.levels; out[15] = c.nc2; out[16] = c.ng2; out[17] = c.nce2; }
+    return cap >= 18 ? 18 : (cap >= 14 ? 14 : 12);
   }
   if (!s->uploaded) { g_err = "nothing uploaded"; return -1; }
   if (nm == "W" || nm == "Wt") {  // de-tiled: [slots][18] in pose-major slot order (W) or plane-major order (Wt)

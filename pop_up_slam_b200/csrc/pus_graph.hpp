@@ -24,8 +24,18 @@ enum FactorKind { F_POSE_PRIOR = 0, F_ODOMETRY = 1, F_POSE_PLANE = 2, F_PLANE_PR
 
 constexpr int kBlockPoses = 16;            // poses per dense preconditioner block
 constexpr int kBlockDim = 6 * kBlockPoses; // 96
-constexpr int kCoarseSpacing = 16;         // base spacing (poses) of the coarse hat-function nodes; multiple of kBlockPoses
-constexpr int kMaxCoarseNodes = 320;       // the spacing grows in steps of 16 so that the dense A_c stays <= 1920^2
+// Three-level additive preconditioner of the reduced pose system:
+//   level 1  exact inverses of the 16-pose diagonal blocks of S
+//   level 2  piecewise-linear ("hat") trajectory modes with one node every kL2Spacing poses, solved by block-Jacobi in
+//            groups of kGroupNodes nodes (96 x 96 blocks of P2^T S P2, same size as the level-1 blocks)
+//   level 3  hat modes with one node every kCoarseSpacing poses, Galerkin operator inverted densely (<= 1920^2)
+// Graphs of up to kL2Spacing * kMaxCoarseNodes = 5120 poses use two levels (1 + an exactly inverted hat level with a node
+// every 16 poses: fewest PCG iterations, dense A_c^-1 <= 1920^2); larger graphs use all three, so the hat level with the
+// fine spacing never has to be inverted (or applied) as a dense matrix and the iteration count stays flat in N.
+constexpr int kL2Spacing = 16;             // = kBlockPoses: every pose block is exactly one level-2 interval
+constexpr int kGroupNodes = 16;            // level-2 nodes per block-Jacobi group (6 * 16 = kBlockDim)
+constexpr int kCoarseSpacing = 128;        // base spacing (poses) of the level-3 nodes; multiple of kBlockPoses
+constexpr int kMaxCoarseNodes = 320;       // the level-3 spacing grows in steps of 128 so that the dense A_c stays <= 1920^2
 constexpr int kHeavyCoarse = 16;           // planes touching more coarse nodes than this are dense rank-3 updates of A_c
 constexpr int kPivotNodes = 8;             // coarse nodes per pivot block of the blocked Gauss-Jordan inversion (48 scalars)
 constexpr int kTile = 32;                  // edges per warp tile
@@ -57,6 +67,7 @@ struct Graph {
   std::vector<HFactor> factors;
   std::string err;
   uint64_t topo_version = 1;  // bumped on any structural edit (node/factor add/remove)
+  int force_levels = 0;       // 0: two or three preconditioner levels by graph size; 2 / 3: forced (tests, studies)
 
   bool ok_node(int id, int kind) const { return id >= 0 && id < (int)nodes.size() && nodes[id].alive && nodes[id].kind == kind; }
   bool ok_factor(int f) const { return f >= 0 && f < (int)factors.size() && factors[f].alive; }
@@ -189,9 +200,16 @@ struct Compiled {
   // coarse (hat) space: (plane, coarse node) pairs
   std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
   std::vector<int> hv_plane, lp_ptr, lp_cea, lp_ceb, fp_ptr, fp_f;   // coarse assembly: heavy planes, per node-pair lists
+  // level 2: (plane, node) pairs at spacing kL2Spacing, and per block-Jacobi group its pairs sorted by (plane, node)
+  int levels = 2;   // preconditioner levels in use (2: SP = 16 k hats inverted exactly; 3: level-2 block-Jacobi + level 3 at SP = 256 k)
+  int nc2 = 0, nce2 = 0, ng2 = 0;
+  std::vector<int> ce2_ptr, ce2_node, ce2_plane, ce2_lo, ce2_hi, g2_ptr, g2_ce;
 };
 
-inline int coarse_spacing(int N) { return kCoarseSpacing * std::max(1, (N + kCoarseSpacing * kMaxCoarseNodes - 1) / (kCoarseSpacing * kMaxCoarseNodes)); }
+inline int coarse_spacing(int N, int levels) {
+  const int base = (levels == 3) ? kCoarseSpacing : kL2Spacing;
+  return base * std::max(1, (N + base * kMaxCoarseNodes - 1) / (base * kMaxCoarseNodes));
+}
 inline int coarse_nodes(int N, int sp) { return N <= 1 ? 1 : (N - 1 + sp - 1) / sp + 1; }
 
 inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
@@ -423,32 +441,54 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     c.grp_info[(size_t)g * 4 + 1] = c.upart_ptr[l];
     c.grp_info[(size_t)g * 4 + 2] = c.upart_ptr[l + 1] - c.upart_ptr[l];
   }
-  // ---- coarse (plane, node) pairs ----
-  c.SP = coarse_spacing(N);
+  // ---- (plane, node) pairs of the two hat levels ----
+  auto build_pairs = [&](int SPx, std::vector<int>& ce_ptr, std::vector<int>& ce_node, std::vector<int>& ce_plane, std::vector<int>& ce_lo,
+                         std::vector<int>& ce_hi) {
+    ce_ptr.assign(M + 1, 0);
+    ce_node.clear(); ce_plane.clear(); ce_lo.clear(); ce_hi.clear();
+    for (int l = 0; l < M; l++) {
+      int s0 = c.pl_ptr[l], s1 = c.pl_ptr[l + 1];
+      int last = -1;
+      for (int s = s0; s < s1; s++) {
+        int p = c.pl_pose[s];
+        int c0 = p / SPx;
+        int cand[2] = {c0, (p % SPx) ? c0 + 1 : -1};
+        for (int q = 0; q < 2; q++) {
+          int nd = cand[q];
+          if (nd < 0 || nd <= last) continue;
+          // slots of plane l supporting node nd: poses in ((nd-1)*SP, (nd+1)*SP)
+          // slots are pose-sorted within the plane: lo = first slot with pose > (nd-1)*SP, hi = first with pose >= (nd+1)*SP
+          const int* pb = c.pl_pose.data();
+          const int lo = (int)(std::upper_bound(pb + s0, pb + s1, (nd - 1) * SPx) - pb);
+          const int hi = (int)(std::lower_bound(pb + lo, pb + s1, (nd + 1) * SPx) - pb);
+          ce_node.push_back(nd); ce_plane.push_back(l); ce_lo.push_back(lo); ce_hi.push_back(hi);
+          last = nd;
+        }
+      }
+      ce_ptr[l + 1] = (int)ce_node.size();
+    }
+  };
+  c.levels = g.force_levels ? g.force_levels : (N > kL2Spacing * kMaxCoarseNodes ? 3 : 2);
+  c.SP = coarse_spacing(N, c.levels);
   const int SPc = c.SP;
   c.nc = coarse_nodes(N, SPc);
   c.nc_pad = (c.nc + kPivotNodes - 1) / kPivotNodes * kPivotNodes;
-  c.ce_ptr.assign(M + 1, 0);
-  for (int l = 0; l < M; l++) {
-    int s0 = c.pl_ptr[l], s1 = c.pl_ptr[l + 1];
-    int last = -1;
-    for (int s = s0; s < s1; s++) {
-      int p = c.pl_pose[s];
-      int c0 = p / SPc;
-      int cand[2] = {c0, (p % SPc) ? c0 + 1 : -1};
-      for (int q = 0; q < 2; q++) {
-        int nd = cand[q];
-        if (nd < 0 || nd <= last) continue;
-        // slots of plane l supporting node nd: poses in ((nd-1)*SP, (nd+1)*SP)
-        // slots are pose-sorted within the plane: lo = first slot with pose > (nd-1)*SP, hi = first with pose >= (nd+1)*SP
-        const int* pb = c.pl_pose.data();
-        const int lo = (int)(std::upper_bound(pb + s0, pb + s1, (nd - 1) * SPc) - pb);
-        const int hi = (int)(std::lower_bound(pb + lo, pb + s1, (nd + 1) * SPc) - pb);
-        c.ce_node.push_back(nd); c.ce_plane.push_back(l); c.ce_lo.push_back(lo); c.ce_hi.push_back(hi);
-        last = nd;
-      }
-    }
-    c.ce_ptr[l + 1] = (int)c.ce_node.size();
+  build_pairs(SPc, c.ce_ptr, c.ce_node, c.ce_plane, c.ce_lo, c.ce_hi);
+  c.nc2 = coarse_nodes(N, kL2Spacing);
+  c.ng2 = (c.nc2 + kGroupNodes - 1) / kGroupNodes;
+  if (c.levels == 3) build_pairs(kL2Spacing, c.ce2_ptr, c.ce2_node, c.ce2_plane, c.ce2_lo, c.ce2_hi);
+  else { c.ce2_ptr.assign(M + 1, 0); c.ce2_node.assign(1, 0); c.ce2_plane.assign(1, 0); c.ce2_lo.assign(1, 0); c.ce2_hi.assign(1, 0); c.ng2 = 0; }
+  c.nce2 = (c.levels == 3) ? (int)c.ce2_node.size() : 0;
+  if (c.levels == 3) {
+    // per group: its pairs in (plane, node) order = the order they already have, restricted to the group's nodes
+    c.g2_ptr.assign(c.ng2 + 1, 0);
+    for (int i = 0; i < c.nce2; i++) c.g2_ptr[c.ce2_node[i] / kGroupNodes + 1]++;
+    for (int gq = 0; gq < c.ng2; gq++) c.g2_ptr[gq + 1] += c.g2_ptr[gq];
+    c.g2_ce.assign(std::max(1, c.nce2), 0);
+    std::vector<int> fill(c.g2_ptr.begin(), c.g2_ptr.end() - 1);
+    for (int i = 0; i < c.nce2; i++) c.g2_ce[fill[c.ce2_node[i] / kGroupNodes]++] = i;
+  } else {
+    c.g2_ptr.assign(1, 0); c.g2_ce.assign(1, 0);
   }
   c.nce = (int)c.ce_node.size();
   c.n2ce_ptr.assign(c.nc + 1, 0);

@@ -85,6 +85,10 @@ struct DevGraph {
   const int *ce_ptr, *ce_node, *ce_plane, *ce_lo, *ce_hi, *n2ce_ptr, *n2ce;
   const int *hv_plane, *lp_ptr, *lp_cea, *lp_ceb, *fp_ptr, *fp_f;
   int n_hv;
+  // three-level preconditioner (large graphs): hat nodes every 16 poses, block-Jacobi in groups of kGroupNodes nodes
+  int levels, nc2, nce2, ng2;
+  const int *ce2_node, *ce2_plane, *ce2_lo, *ce2_hi, *g2_ptr, *g2_ce;
+  double *Wc2, *Yc2, *D2inv, *zc2;
   // work buffers
   double *W, *Wt, *JP, *JL, *PF, *LP;
   double *Hpp, *gp, *Hll, *gl, *Hinv, *vl, *dl;
@@ -110,6 +114,7 @@ struct Ctx {
   unsigned bar_target;   // thread 0 only
   int red_slot;
   int smem_cache_ok;     // the dense-block cache in shared memory holds this solve's blocks
+  int l3_local;          // three-level mode, small level 3: every CTA applies A_3^-1 itself (no exchange of its result)
   int use_tma;           // this graph streams its W / Wt tiles through the per-warp TMA staging buffers
   unsigned tma_par;      // phase parity of this warp's two staging mbarriers (bit s = stage s)
   unsigned gj_par;       // phase parity of the coarse inversion's two panel mbarriers
@@ -424,6 +429,7 @@ __device__ __forceinline__ double gj_entry(Load ld, int ldm, int row, int col, i
 // ---------------------------------------------------------------------------------------------
 // phase timer of the lead thread (CTA 0 of the team, thread 0): %globaltimer deltas accumulated in shared
 // memory (a global read-modify-write per lap would itself cost ~1 us on the critical path) and flushed once.
+constexpr int kL3Local = 192;   // three-level mode: level 3 of at most this many rows is applied by every CTA itself
 constexpr int kSmTimer = 576;  // 24 x u64 inside the first KB of dynamic shared memory
 struct Timer {
   bool on;
@@ -923,16 +929,52 @@ struct Phase {
     if (d < 0) d = -d;
     return d >= G.SP ? 0.0 : 1.0 - (double)d * G.inv_SP;
   }
+  // level-2 hat (a node every kL2Spacing = 16 poses)
+  __device__ __forceinline__ double hat2(int p, int node) const {
+    int d = p - node * kL2Spacing;
+    if (d < 0) d = -d;
+    return d >= kL2Spacing ? 0.0 : 1.0 - (double)d * (1.0 / kL2Spacing);
+  }
+  // hat of the level the residual restrictions (rcpart / qcpart, 12 values per pose block) live on
+  __device__ __forceinline__ double hat_r(int p, int node) const { return G.levels == 3 ? hat2(p, node) : hat(p, node); }
+  __device__ __forceinline__ int sp_r() const { return G.levels == 3 ? kL2Spacing : G.SP; }
+  // coarse part of z at pose p, row: interpolation of the published node vectors (two levels: zc; three: zc2 [+ zc])
+  __device__ __forceinline__ double coarse_z(int p, int row) const {
+    if (G.levels != 3) {
+      const int c0 = p / G.SP;
+      return hat(p, c0) * ldc(G.zc + (size_t)c0 * 6 + row) + hat(p, c0 + 1) * ldc(G.zc + (size_t)min(c0 + 1, G.nc - 1) * 6 + row);
+    }
+    const int a = p / kL2Spacing;
+    const int d = p - a * kL2Spacing;
+    double v = node2_z(a, row);
+    if (d) { const double t = (double)d * (1.0 / kL2Spacing); v = (1.0 - t) * v + t * node2_z(min(a + 1, G.nc2 - 1), row); }
+    return v;
+  }
+  __device__ __forceinline__ double node2_z(int a, int row) const {
+    double v = ldc(G.zc2 + (size_t)a * 6 + row);
+    if (!c.l3_local) {   // level 3 is distributed: its part is interpolated by the consumer
+      const int p = a * kL2Spacing, c0 = p / G.SP;
+      v += hat(p, c0) * ldc(G.zc + (size_t)c0 * 6 + row) + hat(p, c0 + 1) * ldc(G.zc + (size_t)min(c0 + 1, G.nc - 1) * 6 + row);
+    }
+    return v;
+  }
 
   // -------- Schur setup, part 3: coarse pairs Wc = P^T W (warp per (plane, node) pair) --------
   __device__ void coarse_wc() {
+    coarse_wc_level(G.nce, G.ce_node, G.ce_plane, G.ce_lo, G.ce_hi, G.SP, G.inv_SP, G.Wc, G.Yc);
+    if (G.levels == 3) coarse_wc_level(G.nce2, G.ce2_node, G.ce2_plane, G.ce2_lo, G.ce2_hi, kL2Spacing, 1.0 / kL2Spacing, G.Wc2, G.Yc2);
+  }
+  __device__ void coarse_wc_level(int nce, const int* ce_node, const int* ce_plane, const int* ce_lo, const int* ce_hi, int SP, double inv_SP,
+                                  double* Wc, double* Yc) {
     const int lane = threadIdx.x & 31;
-    for (int ce = warp_team(); ce < G.nce; ce += nwarp_team()) {
-      int node = G.ce_node[ce];
+    for (int ce = warp_team(); ce < nce; ce += nwarp_team()) {
+      int node = ce_node[ce];
       double acc[18];
       for (int k = 0; k < 18; k++) acc[k] = 0;
-      for (int s = G.ce_lo[ce] + lane; s < G.ce_hi[ce]; s += 32) {
-        double w = hat(G.pl_pose[s], node);
+      for (int s = ce_lo[ce] + lane; s < ce_hi[ce]; s += 32) {
+        int d = G.pl_pose[s] - node * SP;
+        if (d < 0) d = -d;
+        double w = d >= SP ? 0.0 : 1.0 - (double)d * inv_SP;
         const double* wt = G.Wt + (size_t)(s >> 5) * kWStride + (s & 31);
         for (int k = 0; k < 18; k++) acc[k] += w * ldc(wt + k * 32);
       }
@@ -941,10 +983,10 @@ struct Phase {
         double v = acc[0];
 #pragma unroll
         for (int k = 1; k < 18; k++) if (lane == k) v = acc[k];
-        G.Wc[(size_t)ce * 18 + lane] = v;
+        Wc[(size_t)ce * 18 + lane] = v;
         // Yc = Wc * Hll_d^-1 (6x3), entry (r, b) = lane
         const int r = lane / 3, b = lane - r * 3;
-        const double* Hi = G.Hinv + (size_t)G.ce_plane[ce] * 9;
+        const double* Hi = G.Hinv + (size_t)ce_plane[ce] * 9;
         double y = 0;
 #pragma unroll
         for (int k = 0; k < 3; k++) {
@@ -953,9 +995,87 @@ struct Phase {
           for (int q = 1; q < 18; q++) if (r * 3 + k == q) w = acc[q];
           y += w * ldc(Hi + k * 3 + b);
         }
-        G.Yc[(size_t)ce * 18 + lane] = y;
+        Yc[(size_t)ce * 18 + lane] = y;
       }
     }
+  }
+
+  // -------- Schur setup (three levels): the 96 x 96 diagonal blocks of P2^T S P2 (groups of kGroupNodes level-2 nodes),
+  // assembled and inverted in shared memory by the owning CTA.  Pose part and pose-pose factors: entry-stationary (every
+  // thread owns entries and walks the poses in the node's support); planes: one plane at a time, its (<= 16) nodes inside
+  // the group as a dense rank-3 update from the staged Yc2 / Wc2 rows.  Fixed summation order, no atomics.
+  __device__ void build_groups(double lambda) {
+    constexpr int LD = kLdS;
+    double* S0 = reinterpret_cast<double*>(c.smem + kSmS0);
+    double* S1 = reinterpret_cast<double*>(c.smem + kSmS1);
+    double* Yst = reinterpret_cast<double*>(c.smem + kSmWg);   // [<=16][18]
+    double* Wst = reinterpret_cast<double*>(c.smem + kSmYg);   // [<=16][18]
+    double* TQ = reinterpret_cast<double*>(c.smem + kSmP);
+    int* nloc = reinterpret_cast<int*>(c.smem + kSmHi);        // node of the staged rows, relative to the group
+    const int tid = threadIdx.x;
+    for (int g = c.rank; g < G.ng2; g += c.tsize) {
+      const int a0 = g * kGroupNodes;
+      const int na = min(kGroupNodes, G.nc2 - a0);
+      __syncthreads();
+      for (int idx = tid; idx < kBlockDim * kBlockDim; idx += kThreads) {
+        const int i = idx / kBlockDim, j = idx - i * kBlockDim;
+        const int ai = i / 6, r = i - ai * 6, bj = j / 6, cc = j - bj * 6;
+        double v = 0.0;
+        if (ai >= na || bj >= na) {
+          v = (i == j) ? 1.0 : 0.0;
+        } else {
+          const int a = a0 + ai, b = a0 + bj;
+          const int plo = max(0, (a - 1) * kL2Spacing + 1), phi = min(G.N, (a + 1) * kL2Spacing);
+          for (int p = plo; p < phi; p++) {
+            const double ha = hat2(p, a), hb = hat2(p, b);
+            if (hb != 0.0) {
+              double h = ldc(G.Hpp + (size_t)p * 36 + r * 6 + cc);
+              if (r == cc) h *= (1 + lambda);
+              v += ha * hb * h;
+            }
+            for (int k = G.pinc_ptr[p]; k < G.pinc_ptr[p + 1]; k++) {   // pose-pose blocks of Hpp coupling p to other poses
+              const int inc = G.pinc[k], f = inc >> 1, side = inc & 1;
+              const int jn = G.pf_j[f];
+              if (jn < 0) continue;
+              const int o = side ? G.pf_i[f] : jn;
+              const double ho = hat2(o, b);
+              if (ho == 0.0) continue;
+              const double blk = side ? ldc(G.PF + (size_t)f * 120 + 72 + cc * 6 + r) : ldc(G.PF + (size_t)f * 120 + 72 + r * 6 + cc);
+              v += ha * ho * blk;
+            }
+          }
+        }
+        S0[i * LD + j] = v;
+      }
+      __syncthreads();
+      const int q1 = G.g2_ptr[g + 1];
+      int q = G.g2_ptr[g];
+      while (q < q1) {   // (uniform across the CTA)
+        const int l = G.ce2_plane[G.g2_ce[q]];
+        int qe = q + 1;
+        while (qe < q1 && G.ce2_plane[G.g2_ce[qe]] == l) qe++;
+        const int m = qe - q;
+        for (int i = tid; i < m * 18; i += kThreads) {
+          const int ce = G.g2_ce[q + i / 18];
+          Yst[i] = ldc(G.Yc2 + (size_t)ce * 18 + i % 18);
+          Wst[i] = ldc(G.Wc2 + (size_t)ce * 18 + i % 18);
+        }
+        if (tid < m) nloc[tid] = G.ce2_node[G.g2_ce[q + tid]] - a0;
+        __syncthreads();
+        for (int idx = tid; idx < m * m * 36; idx += kThreads) {
+          const int mi = idx / (36 * m), rem = idx - mi * 36 * m, mj = rem / 36, en = rem - mj * 36, r = en / 6, cc = en - r * 6;
+          const double* y = Yst + mi * 18 + r * 3;
+          const double* w = Wst + mj * 18 + cc * 3;
+          S0[(nloc[mi] * 6 + r) * LD + nloc[mj] * 6 + cc] -= y[0] * w[0] + y[1] * w[1] + y[2] * w[2];
+        }
+        __syncthreads();
+        q = qe;
+      }
+      const double* inv = gj_invert_smem<kBlockDim / 8, LD>(S0, S1, TQ);
+      double* out = G.D2inv + (size_t)g * kBlockDim * kBlockDim;
+      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) out[i] = inv[(i / kBlockDim) * LD + i % kBlockDim];
+    }
+    __syncthreads();
   }
 
   // -------- Schur setup, part 4: A_c = P^T S P, one warp per coarse row panel --------
@@ -1251,11 +1371,15 @@ struct Phase {
         for (int a = 0; a < 6; a++) x[a] = ldc(va + (size_t)p * 6 + a);
         if (vb) for (int a = 0; a < 6; a++) x[a] += beta * ldc(vb + (size_t)p * 6 + a);
         if (zc) {
-          const int c0 = p / G.SP;
-          const double h0 = hat(p, c0), h1 = hat(p, c0 + 1);
-          const double* z0 = zc + (size_t)c0 * 6;
-          const double* z1 = zc + (size_t)min(c0 + 1, G.nc - 1) * 6;
-          for (int a = 0; a < 6; a++) x[a] += h0 * ldc(z0 + a) + h1 * ldc(z1 + a);
+          if (G.levels != 3) {
+            const int c0 = p / G.SP;
+            const double h0 = hat(p, c0), h1 = hat(p, c0 + 1);
+            const double* z0 = zc + (size_t)c0 * 6;
+            const double* z1 = zc + (size_t)min(c0 + 1, G.nc - 1) * 6;
+            for (int a = 0; a < 6; a++) x[a] += h0 * ldc(z0 + a) + h1 * ldc(z1 + a);
+          } else {
+            for (int a = 0; a < 6; a++) x[a] += coarse_z(p, a);
+          }
         }
         const double* wt = G.Wt + (size_t)tile * kWStride + lane;
 #pragma unroll
@@ -1361,9 +1485,9 @@ struct Phase {
   __device__ __forceinline__ void restrict_block(const double* sv, int slot, int u, int k, int np, double* out) {
     if (u < 12 && k < G.nblk) {
       int node = u / 6, row = u % 6;
-      int p0 = k * kBlockPoses, c0 = p0 / G.SP;
+      int p0 = k * kBlockPoses, c0 = p0 / sp_r();
       double acc = 0;
-      for (int pi = 0; pi < np; pi++) acc += hat(p0 + pi, c0 + node) * sv[slot * kBlockDim + pi * 6 + row];
+      for (int pi = 0; pi < np; pi++) acc += hat_r(p0 + pi, c0 + node) * sv[slot * kBlockDim + pi * 6 + row];
       put(c, &out[(size_t)k * 12 + u], acc);
     }
   }
@@ -1377,9 +1501,7 @@ struct Phase {
       if (slot < kSlots && k < G.nblk && p < G.N) {
         const int row = u % 6;
         size_t o = (size_t)p * 6 + row;
-        const int c0 = p / G.SP;
-        put(c, &G.pv[cur ^ 1][o], ldc(G.z + o) + beta * ldc(G.pv[cur] + o) + hat(p, c0) * ldc(G.zc + (size_t)c0 * 6 + row) +
-                           hat(p, c0 + 1) * ldc(G.zc + (size_t)min(c0 + 1, G.nc - 1) * 6 + row));
+        put(c, &G.pv[cur ^ 1][o], ldc(G.z + o) + beta * ldc(G.pv[cur] + o) + coarse_z(p, row));
       }
     }
   }
@@ -1621,6 +1743,106 @@ struct Phase {
     __syncthreads();
   }
 
+  // -------- three-level preconditioner, coarse part: level-3 residual from the level-2 partials; level-3 rows (distributed
+  // over the team, or applied by every CTA when the level is small); level-2 nodes: one warp per node = its 6 rows of the
+  // group's 96 x 96 inverse.  Publishes zc2 (and zc when level 3 is distributed); returns the partial of r.z it owns.
+  __device__ double coarse_three_level(double alpha, int acinv, const double* rc_old, bool first) {
+    double* src = reinterpret_cast<double*>(c.smem + kSmRc);   // level-3 residual [6 nc]
+    double* z3s = reinterpret_cast<double*>(c.smem + kSmZc);   // level-3 solution when it is applied locally (<= kL3Local rows)
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int ldm = 6 * G.nc, m = G.SP / kL2Spacing;
+    // level-2 residual of node a: per-block partials of the previous iteration, updated linearly (r_new = r - alpha q)
+    auto rc2 = [&](int a, int row) -> double {
+      double v = 0.0;
+      if (a < G.nblk) {
+        v += ldc(rc_old + (size_t)a * 12 + row);
+        if (!first) v -= alpha * ldc(G.qcpart + (size_t)a * 12 + row);
+      }
+      if (a >= 1) {
+        v += ldc(rc_old + (size_t)(a - 1) * 12 + 6 + row);
+        if (!first) v -= alpha * ldc(G.qcpart + (size_t)(a - 1) * 12 + 6 + row);
+      }
+      return v;
+    };
+    __syncthreads();
+    for (int i = tid; i < ldm; i += kThreads) {
+      const int A = i / 6, row = i - A * 6;
+      const int alo = max(0, (A - 1) * m + 1), ahi = min(G.nc2, (A + 1) * m);
+      double acc = 0.0;
+      for (int a = alo; a < ahi; a++) {
+        int d = a - A * m;
+        if (d < 0) d = -d;
+        acc += (1.0 - (double)d / (double)m) * rc2(a, row);
+      }
+      src[i] = acc;
+    }
+    __syncthreads();
+    lap(13);
+    const double* Ai = G.Ac[acinv];
+    double dot = 0.0;
+    if (c.l3_local) {
+      for (int i = tid >> 5; i < ldm; i += kWarps) {
+        const double* arow = Ai + ac_index(G.ldmc, i, 0);
+        double acc = 0.0;
+        for (int j = lane; j < ldm; j += 32) acc += ldc(arow + (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk)) * src[j];
+        acc = warp_sum(acc);
+        if (lane == 0) {
+          z3s[i] = acc;
+          if (c.rank == 0) dot += src[i] * acc;
+        }
+      }
+      __syncthreads();
+    } else {
+      const int nw = nwarp_team();
+      for (int i = warp_team(); i < ldm; i += nw) {
+        const double* arow = Ai + ac_index(G.ldmc, i, 0);
+        double acc = 0.0;
+        int j = lane;
+        for (; j + 32 * 7 < ldm; j += 32 * 8) {
+          double av[8];
+#pragma unroll
+          for (int t = 0; t < 8; t++) {
+            const int jj = j + 32 * t;
+            av[t] = ldc(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk));
+          }
+#pragma unroll
+          for (int t = 0; t < 8; t++) acc += av[t] * src[j + 32 * t];
+        }
+        for (; j < ldm; j += 32) acc += ldc(arow + (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk)) * src[j];
+        acc = warp_sum(acc);
+        if (lane == 0) { put(c, &G.zc[i], acc); dot += src[i] * acc; }
+      }
+    }
+    const int nw2 = nwarp_team();
+    for (int a = warp_team(); a < G.nc2; a += nw2) {
+      const int g = a / kGroupNodes, a0 = g * kGroupNodes;
+      double rg[3];
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const int e = lane + 32 * t, an = a0 + e / 6, row = e % 6;
+        rg[t] = (an < G.nc2) ? rc2(an, row) : 0.0;
+      }
+      const double* D = G.D2inv + (size_t)g * kBlockDim * kBlockDim + (size_t)((a - a0) * 6) * kBlockDim;
+      for (int rr = 0; rr < 6; rr++) {
+        double acc = ldc(D + rr * kBlockDim + lane) * rg[0] + ldc(D + rr * kBlockDim + lane + 32) * rg[1] + ldc(D + rr * kBlockDim + lane + 64) * rg[2];
+        acc = warp_sum(acc);
+        const int e = (a - a0) * 6 + rr;
+        const double sel = (e < 32) ? rg[0] : (e < 64 ? rg[1] : rg[2]);
+        const double rme = __shfl_sync(0xffffffffu, sel, e & 31);
+        if (lane == 0) {
+          double zv = acc;
+          dot += rme * acc;
+          if (c.l3_local) {
+            const int p = a * kL2Spacing, c0 = p / G.SP;
+            zv += hat(p, c0) * z3s[c0 * 6 + rr] + hat(p, c0 + 1) * z3s[min(c0 + 1, G.nc - 1) * 6 + rr];
+          }
+          put(c, &G.zc2[(size_t)a * 6 + rr], zv);
+        }
+      }
+    }
+    return dot;
+  }
+
   // -------- PCG: x += alpha p ; r -= alpha q ; z = M^-1 r (dense block + coarse) ; returns partial r.z ----
   // rc_old / rc_new: ping-pong buffers of per-block coarse restrictions of r
   __device__ double precondition(double alpha, const double* pvec, int acinv, const double* rc_old, double* rc_new,
@@ -1630,93 +1852,97 @@ struct Phase {
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
     const int ldm = 6 * G.nc;
     const int bpn = G.SP / kBlockPoses;  // blocks per coarse interval
-    // full coarse residual rc = sum_k rc_old[k] - alpha * sum_k qcpart[k]  (linear in r)
-    __syncthreads();
-    if (bpn == 1) {
-      // one block per coarse interval (graphs up to 5120 poses): block `node` feeds the node through its slot 0,
-      // block `node-1` through slot 1; four outputs per thread so that all 16 loads are in flight together
-      for (int i0 = tid; i0 < ldm; i0 += 4 * kThreads) {
-        double va[4][2], vq[4][2];
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-          const int i = i0 + m * kThreads, node = i / 6, row = i - node * 6;
-#pragma unroll
-          for (int side = 0; side < 2; side++) {
-            const int k = node - side;
-            const bool ok = (i < ldm) && (k >= 0) && (k < G.nblk);
-            va[m][side] = ok ? ldc(rc_old + (size_t)k * 12 + side * 6 + row) : 0.0;
-            vq[m][side] = (ok && !first) ? ldc(G.qcpart + (size_t)k * 12 + side * 6 + row) : 0.0;
+    double dot = 0;
+    if (G.levels == 3) {
+      dot = coarse_three_level(alpha, acinv, rc_old, first);
+    } else {
+      // full coarse residual rc = sum_k rc_old[k] - alpha * sum_k qcpart[k]  (linear in r)
+      __syncthreads();
+      if (bpn == 1) {
+        // one block per coarse interval (graphs up to 5120 poses): block `node` feeds the node through its slot 0,
+        // block `node-1` through slot 1; four outputs per thread so that all 16 loads are in flight together
+        for (int i0 = tid; i0 < ldm; i0 += 4 * kThreads) {
+          double va[4][2], vq[4][2];
+  #pragma unroll
+          for (int m = 0; m < 4; m++) {
+            const int i = i0 + m * kThreads, node = i / 6, row = i - node * 6;
+  #pragma unroll
+            for (int side = 0; side < 2; side++) {
+              const int k = node - side;
+              const bool ok = (i < ldm) && (k >= 0) && (k < G.nblk);
+              va[m][side] = ok ? ldc(rc_old + (size_t)k * 12 + side * 6 + row) : 0.0;
+              vq[m][side] = (ok && !first) ? ldc(G.qcpart + (size_t)k * 12 + side * 6 + row) : 0.0;
+            }
+          }
+  #pragma unroll
+          for (int m = 0; m < 4; m++) {
+            const int i = i0 + m * kThreads;
+            if (i < ldm) src[i] = (0.0 + (va[m][0] - alpha * vq[m][0])) + (va[m][1] - alpha * vq[m][1]);
           }
         }
-#pragma unroll
-        for (int m = 0; m < 4; m++) {
-          const int i = i0 + m * kThreads;
-          if (i < ldm) src[i] = (0.0 + (va[m][0] - alpha * vq[m][0])) + (va[m][1] - alpha * vq[m][1]);
-        }
-      }
-    } else
-    for (int i = tid; i < ldm; i += kThreads) {
-      int node = i / 6, row = i % 6;
-      // blocks with c0 == node feed `node` through their slot 0, blocks with c0 == node-1 through slot 1;
-      // issue all loads before the (fixed-order) sums
-      double va[2][8], vq[2][8];
-#pragma unroll
-      for (int side = 0; side < 2; side++) {
-        int cint = node - side;
-        int k0 = cint * bpn;
-#pragma unroll
-        for (int t = 0; t < 8; t++) {
-          int k = k0 + t;
-          bool ok = (cint >= 0) && (t < bpn) && (k < G.nblk);
-          va[side][t] = ok ? ldc(rc_old + (size_t)k * 12 + side * 6 + row) : 0.0;
-          vq[side][t] = (ok && !first) ? ldc(G.qcpart + (size_t)k * 12 + side * 6 + row) : 0.0;
-        }
-      }
-      double acc = 0;
-#pragma unroll
-      for (int side = 0; side < 2; side++)
-#pragma unroll
-        for (int t = 0; t < 8; t++) acc += va[side][t] - alpha * vq[side][t];
-      if (bpn > 8) {  // (spacing > 128 poses: rare large graphs) remaining blocks, plain loop
+      } else
+      for (int i = tid; i < ldm; i += kThreads) {
+        int node = i / 6, row = i % 6;
+        // blocks with c0 == node feed `node` through their slot 0, blocks with c0 == node-1 through slot 1;
+        // issue all loads before the (fixed-order) sums
+        double va[2][8], vq[2][8];
+  #pragma unroll
         for (int side = 0; side < 2; side++) {
           int cint = node - side;
-          if (cint < 0) continue;
-          int k0 = cint * bpn + 8, k1 = min(G.nblk, cint * bpn + bpn);
-          for (int k = k0; k < k1; k++) {
-            double v = ldc(rc_old + (size_t)k * 12 + side * 6 + row);
-            if (!first) v -= alpha * ldc(G.qcpart + (size_t)k * 12 + side * 6 + row);
-            acc += v;
+          int k0 = cint * bpn;
+  #pragma unroll
+          for (int t = 0; t < 8; t++) {
+            int k = k0 + t;
+            bool ok = (cint >= 0) && (t < bpn) && (k < G.nblk);
+            va[side][t] = ok ? ldc(rc_old + (size_t)k * 12 + side * 6 + row) : 0.0;
+            vq[side][t] = (ok && !first) ? ldc(G.qcpart + (size_t)k * 12 + side * 6 + row) : 0.0;
           }
         }
-      }
-      src[i] = acc;
-    }
-    __syncthreads();
-    lap(13);
-    const double* Ai = G.Ac[acinv];
-    double dot = 0;
-    // coarse part, distributed over the team: one warp per row of A_c^-1.  z is never formed with its coarse
-    // part; r.z = r.z_local + rc.zc (rc = P^T r), and the consumers of z add P*zc on the fly.
-    {
-      const int lane = tid & 31;
-      const int nw = nwarp_team();
-      for (int i = warp_team(); i < ldm; i += nw) {
-        const double* arow = Ai + ac_index(G.ldmc, i, 0);
         double acc = 0;
-        int j = lane;
-        for (; j + 32 * 15 < ldm; j += 32 * 16) {   // 16 loads per lane in flight
-          double av[16];
-#pragma unroll
-          for (int t = 0; t < 16; t++) {
-            const int jj = j + 32 * t;
-            av[t] = ldc(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk));
+  #pragma unroll
+        for (int side = 0; side < 2; side++)
+  #pragma unroll
+          for (int t = 0; t < 8; t++) acc += va[side][t] - alpha * vq[side][t];
+        if (bpn > 8) {  // (spacing > 128 poses: rare large graphs) remaining blocks, plain loop
+          for (int side = 0; side < 2; side++) {
+            int cint = node - side;
+            if (cint < 0) continue;
+            int k0 = cint * bpn + 8, k1 = min(G.nblk, cint * bpn + bpn);
+            for (int k = k0; k < k1; k++) {
+              double v = ldc(rc_old + (size_t)k * 12 + side * 6 + row);
+              if (!first) v -= alpha * ldc(G.qcpart + (size_t)k * 12 + side * 6 + row);
+              acc += v;
+            }
           }
-#pragma unroll
-          for (int t = 0; t < 16; t++) acc += av[t] * src[j + 32 * t];
         }
-        for (; j < ldm; j += 32) acc += ldc(arow + (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk)) * src[j];
-        acc = warp_sum(acc);
-        if (lane == 0) { put(c, &G.zc[i], acc); dot += src[i] * acc; }
+        src[i] = acc;
+      }
+      __syncthreads();
+      lap(13);
+      const double* Ai = G.Ac[acinv];
+      // coarse part, distributed over the team: one warp per row of A_c^-1.  z is never formed with its coarse
+      // part; r.z = r.z_local + rc.zc (rc = P^T r), and the consumers of z add P*zc on the fly.
+      {
+        const int lane = tid & 31;
+        const int nw = nwarp_team();
+        for (int i = warp_team(); i < ldm; i += nw) {
+          const double* arow = Ai + ac_index(G.ldmc, i, 0);
+          double acc = 0;
+          int j = lane;
+          for (; j + 32 * 15 < ldm; j += 32 * 16) {   // 16 loads per lane in flight
+            double av[16];
+  #pragma unroll
+            for (int t = 0; t < 16; t++) {
+              const int jj = j + 32 * t;
+              av[t] = ldc(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk));
+            }
+  #pragma unroll
+            for (int t = 0; t < 16; t++) acc += av[t] * src[j + 32 * t];
+          }
+          for (; j < ldm; j += 32) acc += ldc(arow + (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk)) * src[j];
+          acc = warp_sum(acc);
+          if (lane == 0) { put(c, &G.zc[i], acc); dot += src[i] * acc; }
+        }
       }
     }
     lap(14);

@@ -95,6 +95,46 @@ def test_tma_staged_tiles_match_direct_loads():
     assert np.abs(res[0][1] - res[1][1]).max() <= 1e-9
 
 
+@pytest.mark.parametrize("cfg,kw,flags", [(2, {}, 8), (3, dict(n_poses=700, n_planes=70, max_iterations=8), 8),
+                                          (3, dict(n_poses=900, n_planes=90, max_iterations=8), 8 | 2),
+                                          (3, dict(n_poses=4200, n_planes=420, max_iterations=5), 8)])
+def test_three_level_preconditioner_matches_oracle(cfg, kw, flags):
+    """the large-graph preconditioner (16-pose blocks + block-Jacobi on the hat nodes every 16 poses + a dense level on hat
+    nodes every 128 poses) forced on small graphs (solver option reserved[2] bit 3), alone and together with the
+    bulk-copy-staged data path (bit 1): a preconditioner changes the PCG iteration count, never the solution -- same LM
+    trace and estimates as the oracle and as the two-level solve; 4 200 poses = 17 level-3 nodes and 264 level-2 nodes in
+    17 groups."""
+    import ctypes
+    g = gg.make_config(cfg, seed=2, **kw)
+    orc = OracleAPI()
+    orc.set_jacobian_mode(1)
+    io = gg.build_bulk(orc, g)
+    gg.configure(orc, g)
+    it_o = orc.batch_optimize()
+    res = []
+    for fl in (flags & 2, flags):
+        gpu = GpuGraphAPI()
+        ig = gg.build_bulk(gpu, g)
+        gg.configure(gpu, g)
+        o = gpu.get_solver_options()
+        o.reserved[2] = fl
+        gpu._chk(gpu.lib.pus_set_solver_options(gpu.h, ctypes.byref(o)))
+        assert gpu.batch_optimize() == it_o
+        npcg = gpu.stats()["pcg_iterations"]
+        acc = orc.trace()["accepted"] == 1
+        assert np.array_equal(gpu.trace()["accepted"], orc.trace()["accepted"])
+        assert np.allclose(gpu.trace()["chi2_new"][acc], orc.trace()["chi2_new"][acc], rtol=1e-6)
+        assert np.allclose(gpu.trace()["chi2_new"], orc.trace()["chi2_new"], rtol=1e-4)    # (rejected trial steps: ill-conditioned)
+        compare(gpu, orc, ig, io)
+        dims = gpu.debug_fetch("dims", 18)
+        res.append((gpu.chi2(), gpu.get_poses(ig["pose_ids"]), npcg, int(dims[14])))
+    assert res[0][3] == 2 and res[1][3] == 3
+    assert abs(res[0][0] - res[1][0]) <= 1e-7 * abs(res[0][0])     # (both PCG solves stop at 1e-8)
+    assert np.abs(res[0][1] - res[1][1]).max() <= 1e-6
+    print("PCG iterations two-level / three-level:", res[0][2], res[1][2])
+    assert res[1][2] <= 3 * res[0][2] + 20    # (the three-level scheme needs somewhat more iterations on small graphs)
+
+
 def test_repeated_observations_of_one_plane():
     """a pose that observes the same plane twice (the reference allows it: Mapping.cpp adds a factor per matched
     segment) takes the general dense-block build path instead of the pose-pair fast path; same answer as the oracle."""
@@ -153,7 +193,9 @@ def test_large_graph_streaming_path():
 
 
 @pytest.mark.parametrize("cfg,world,kw", [(2, 2, {}), (2, 3, {}), (3, 2, dict(n_poses=600, n_planes=60, max_iterations=8)),
-                                          (3, 2, dict(n_poses=700, n_planes=70, max_iterations=6, force_large_path=True))])
+                                          (3, 2, dict(n_poses=700, n_planes=70, max_iterations=6, force_large_path=True)),
+                                          (3, 2, dict(n_poses=700, n_planes=70, max_iterations=6, three_level=True)),
+                                          (3, 3, dict(n_poses=700, n_planes=70, max_iterations=6, force_large_path=True, three_level=True))])
 def test_one_graph_spanning_ranks_emulated(cfg, world, kw):
     """SURVEY 8e, second bullet: one graph split over several ranks.  The protocol (global ownership of tiles / blocks
     / coarse rows, mirrored stores into every rank's arena, cross-rank barrier, replicated LM driver) run with `world`
@@ -161,11 +203,12 @@ def test_one_graph_spanning_ranks_emulated(cfg, world, kw):
     import ctypes
     kw = dict(kw)
     large = kw.pop("force_large_path", False)   # the large-graph data path (bulk-copy staging, published direction, heavy planes)
+    three = kw.pop("three_level", False)        # the large-graph (three-level) preconditioner
 
     def options(api):
-        if large:
+        if large or three:
             o = api.get_solver_options()
-            o.reserved[2] = 2
+            o.reserved[2] = (2 if large else 0) | (8 if three else 0)
             api._chk(api.lib.pus_set_solver_options(api.h, ctypes.byref(o)))
 
     g = gg.make_config(cfg, seed=1, **kw)

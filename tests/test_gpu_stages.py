@@ -145,3 +145,55 @@ def test_chi2_matches_oracle():
     gpu, orc, ig, io = make_pair(g)
     c_g, c_o = gpu.chi2(), orc.chi2()
     assert abs(c_g - c_o) <= 1e-11 * c_o
+
+
+def hat_matrix(N, spc):
+    nc = (N - 1 + spc - 1) // spc + 1
+    P = np.zeros((6 * N, 6 * nc))
+    for p in range(N):
+        c0, t = p // spc, (p % spc) / spc
+        for d in range(6):
+            P[6 * p + d, 6 * c0 + d] = 1 - t
+            if t > 0:
+                P[6 * p + d, 6 * (c0 + 1) + d] = t
+    return P, nc
+
+
+def test_three_level_preconditioner_pieces():
+    """the large-graph preconditioner forced on a small corridor (solver option reserved[2] bit 3): the level-2 groups are
+    the inverted 96 x 96 diagonal blocks of P2^T S P2 (hat nodes every 16 poses, 16 nodes per group) and level 3 is the
+    inverse of P3^T S P3 (hat nodes every 128 poses), both against numpy on the oracle's normal equations."""
+    import ctypes
+    g = small_graph(seed=4, n_poses=610, n_planes=60)
+    gpu, orc, ig, io = make_pair(g)
+    o = gpu.get_solver_options()
+    o.reserved[2] = 8
+    gpu._chk(gpu.lib.pus_set_solver_options(gpu.h, ctypes.byref(o)))
+    N = g.n_poses
+    lam = 1e-3
+    A, b, S = schur_reference(orc, g, lam)
+    gpu.upload()
+    gpu.debug_run_stage(1, lam)
+    dims = gpu.debug_fetch("dims", 18).astype(int)
+    assert dims[14] == 3 and dims[12] == 128
+    P2, nc2 = hat_matrix(N, 16)
+    assert dims[15] == nc2
+    A2 = P2.T @ S @ P2
+    ng = (nc2 + 15) // 16
+    D2inv = gpu.debug_fetch("D2inv", ng * 96 * 96).reshape(ng, 96, 96)
+    for k in range(ng):
+        lo, hi = 96 * k, min(96 * (k + 1), 6 * nc2)
+        ref = np.linalg.inv(A2[lo:hi, lo:hi])
+        assert relerr(D2inv[k][:hi - lo, :hi - lo], ref) < 1e-7, k
+        assert np.allclose(D2inv[k][hi - lo:, hi - lo:], np.eye(96 - (hi - lo)))
+    P3, nc3 = hat_matrix(N, 128)
+    A3 = P3.T @ S @ P3
+    ncp = (nc3 + 7) // 8 * 8
+    Acinv = gpu.debug_fetch("Acinv", 36 * ncp * ncp).reshape(6 * ncp, 6 * ncp)
+    assert relerr(Acinv[:6 * nc3, :6 * nc3], np.linalg.inv(A3)) < 1e-7
+    # and the whole solve with it
+    ref = orc.solve_step(lam)
+    gpu.debug_run_stage(2, lam)
+    got = np.concatenate([gpu.debug_fetch("x", 6 * N), gpu.debug_fetch("dl", 3 * g.n_planes)])
+    assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-7
+    print("three-level PCG iterations on the 610-pose corridor:", gpu.stats()["pcg_iterations"])
