@@ -229,7 +229,7 @@ static int upload(Solver* s) {
           {&d.vl, M * 3, "vl"}, {&d.dl, M * 3, "dl"}, {&d.upart, (size_t)c.n_upart * 3, "upart"},
           {&d.x, N * 6, "x"}, {&d.r, N * 6, "r"}, {&d.z, N * 6, "z"}, {&d.q, N * 6, "q"}, {&d.b, N * 6, "b"},
           {&d.pv[0], N * 6, "pv0"}, {&d.pv[1], N * 6, "pv1"}, {&d.xprev, N * 6, "xprev"}, {&d.zc, (size_t)6 * c.nc, "zc"},
-          {&d.zc2, (size_t)6 * c.nc2, "zc2"},
+          {&d.zc2, (size_t)6 * c.nc2, "zc2"}, {&d.rc3, (size_t)6 * c.nc, "rc3"},
           {&d.rcpart[0], (size_t)c.nblk * 12, "rcpart0"}, {&d.rcpart[1], (size_t)c.nblk * 12, "rcpart1"},
           {&d.qcpart, (size_t)c.nblk * 12, "qcpart"}, {&d.red, (size_t)4 * 4 * 2048, "red"}};
       size_t total = 32;   // first 256 bytes: the cross-rank barrier counter and its persisted target

@@ -88,7 +88,7 @@ struct DevGraph {
   // three-level preconditioner (large graphs): hat nodes every 16 poses, block-Jacobi in groups of kGroupNodes nodes
   int levels, nc2, nce2, ng2;
   const int *ce2_node, *ce2_plane, *ce2_lo, *ce2_hi, *g2_ptr, *g2_ce;
-  double *Wc2, *Yc2, *D2inv, *zc2;
+  double *Wc2, *Yc2, *D2inv, *zc2, *rc3;
   // work buffers
   double *W, *Wt, *JP, *JL, *PF, *LP;
   double *Hpp, *gp, *Hll, *gl, *Hinv, *vl, *dl;
@@ -1765,16 +1765,39 @@ struct Phase {
       return v;
     };
     __syncthreads();
-    for (int i = tid; i < ldm; i += kThreads) {
-      const int A = i / 6, row = i - A * 6;
-      const int alo = max(0, (A - 1) * m + 1), ahi = min(G.nc2, (A + 1) * m);
-      double acc = 0.0;
-      for (int a = alo; a < ahi; a++) {
-        int d = a - A * m;
-        if (d < 0) d = -d;
-        acc += (1.0 - (double)d / (double)m) * rc2(a, row);
+    // level-3 residual, one warp per level-3 node: lanes = the level-2 nodes in its support (all their partial loads in flight
+    // together), fixed-order shuffle tree per row.  Small level 3: every CTA assembles all of it (no exchange).  Large graphs:
+    // the nodes are distributed over the team (assembling all of it in every CTA costs 24 loads per level-2 node per CTA --
+    // 75 k loads on 50 k poses), published, and read back behind one extra team barrier.
+    {
+      const int w0 = c.l3_local ? (tid >> 5) : warp_team(), wstep = c.l3_local ? kWarps : nwarp_team();
+      for (int A = w0; A < G.nc; A += wstep) {
+        const int alo = max(0, (A - 1) * m + 1), ahi = min(G.nc2, (A + 1) * m);
+        double acc[6] = {0, 0, 0, 0, 0, 0};
+        for (int a = alo + lane; a < ahi; a += 32) {
+          int d = a - A * m;
+          if (d < 0) d = -d;
+          const double h = 1.0 - (double)d / (double)m;
+          double v[6];
+#pragma unroll
+          for (int row = 0; row < 6; row++) v[row] = rc2(a, row);
+#pragma unroll
+          for (int row = 0; row < 6; row++) acc[row] += h * v[row];
+        }
+#pragma unroll
+        for (int row = 0; row < 6; row++) acc[row] = warp_sum(acc[row]);
+        if (lane < 6) {
+          double v = acc[0];
+#pragma unroll
+          for (int row = 1; row < 6; row++) if (lane == row) v = acc[row];
+          if (c.l3_local) src[A * 6 + lane] = v;
+          else put(c, &G.rc3[A * 6 + lane], v);
+        }
       }
-      src[i] = acc;
+    }
+    if (!c.l3_local) {
+      team_barrier(c);
+      for (int i = tid; i < ldm; i += kThreads) src[i] = ldc(G.rc3 + i);
     }
     __syncthreads();
     lap(13);
