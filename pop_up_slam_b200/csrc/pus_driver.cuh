@@ -333,6 +333,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
     unsigned long long* gbar = reinterpret_cast<unsigned long long*>(smem + kSmGjBar);
     mbar_init(gbar, 1);
     mbar_init(gbar + 1, 1);
+    mbar_init(gbar + 2, 1);
   }
   if ((threadIdx.x & 31) == 0) {
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + kSmBar) + (threadIdx.x >> 5) * 2;

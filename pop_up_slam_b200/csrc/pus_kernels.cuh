@@ -305,11 +305,11 @@ static_assert(kSmPoseEnd <= kSmCache, "pose-phase buffers overlap the block cach
 // TMA staging (large graphs; replaces the block cache): per warp two 4608-byte W / Wt tiles, filled by
 // cp.async.bulk and signalled through one mbarrier per stage
 constexpr int kSmBar = 768;                           // [kWarps][2] mbarriers (u64)
-constexpr int kSmGjBar = 1024;                        // two mbarriers of the coarse inversion's panel pipeline
+constexpr int kSmGjBar = 1024;                        // mbarriers of the coarse inversion's panel pipeline (2) / the block ring (3)
 constexpr int kSmTma = kSmCache;
 constexpr int kTileBytes = 18 * 32 * 8;
 constexpr int kSmTmaEnd = kSmTma + kWarps * 2 * kTileBytes;
-static_assert(kSmBar + kWarps * 2 * 8 <= kSmGjBar && kSmGjBar + 16 <= kSmWork, "mbarriers overlap the work area");
+static_assert(kSmBar + kWarps * 2 * 8 <= kSmGjBar && kSmGjBar + 32 <= kSmWork, "mbarriers overlap the work area");
 static_assert(kSmTmaEnd <= 227 * 1024, "TMA staging buffers");
 static_assert(kSmemBytes <= 227 * 1024, "dynamic shared memory");
 
@@ -917,8 +917,12 @@ struct Phase {
       __syncthreads();
       // inversion in shared memory (S0 <-> S1), then the dense copy for the PCG
       const double* inv = gj_invert_smem<kBlockDim / 8, LD>(S0, S1, TQ);
-      double* out = G.Binv + (size_t)k * kBlockDim * kBlockDim;
-      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) out[i] = inv[(i / kBlockDim) * LD + i % kBlockDim];
+      // packed upper triangle (row i holds the entries j >= i): half the bytes the PCG streams, and exactly symmetric
+      double* out = G.Binv + (size_t)k * kPackedBlock;
+      for (int idx = tid; idx < kBlockDim * kBlockDim; idx += kThreads) {
+        const int i = idx / kBlockDim, j = idx - i * kBlockDim;
+        if (j >= i) out[i * kBlockDim - (i * (i - 1)) / 2 + (j - i)] = inv[i * LD + j];
+      }
     }
     fence_proxy_async();  // Binv is streamed by bulk copies in precondition() on large graphs
     __syncthreads();
@@ -1734,11 +1738,8 @@ struct Phase {
       // cached block ci of this CTA = owned block of (slot = ci % kSlots, round = ci / kSlots)
       int k = c.rank + c.tsize * ((ci % kSlots) + kSlots * (ci / kSlots));
       if (k >= G.nblk) continue;
-      const double* B = G.Binv + (size_t)k * kBlockDim * kBlockDim;
-      for (int idx = threadIdx.x; idx < kBlockDim * kBlockDim; idx += kThreads) {
-        int i = idx / kBlockDim, j = idx - i * kBlockDim;
-        if (j >= i) cache[(size_t)ci * kPackedBlock + i * kBlockDim - (i * (i - 1)) / 2 + (j - i)] = ldc(B + idx);
-      }
+      const double* B = G.Binv + (size_t)k * kPackedBlock;
+      for (int idx = threadIdx.x; idx < kPackedBlock; idx += kThreads) cache[(size_t)ci * kPackedBlock + idx] = ldc(B + idx);
     }
     __syncthreads();
   }
@@ -2007,31 +2008,41 @@ struct Phase {
       __syncthreads();
       unsigned long long* gbar = reinterpret_cast<unsigned long long*>(c.smem + kSmGjBar);
       double* bbuf = reinterpret_cast<double*>(c.smem + kSmTma);
-      constexpr unsigned kBlockBytes = kBlockDim * kBlockDim * 8;
-      static_assert(2 * kBlockBytes <= kSmTmaEnd - kSmTma, "two dense blocks must fit the staging area");
+      constexpr unsigned kBlockBytes = kPackedBlock * 8;   // packed upper triangle: 37 248 bytes, one bulk copy
+      static_assert(kBlockBytes % 16 == 0 && 2 * kBlockBytes <= kSmTmaEnd - kSmTma, "two packed blocks must fit the staging area");
       const int nown = (G.nblk - c.rank + c.tsize - 1) / c.tsize;   // owned blocks: k = rank + tsize * ib
-      if (tid == 0 && nown > 0) tma_load_1d(bbuf, G.Binv + (size_t)c.rank * kBlockDim * kBlockDim, kBlockBytes, gbar);
+      // three-stage ring of 37 KB packed blocks: two bulk copies in flight while one block is applied
+      static_assert(3 * kBlockBytes <= kSmTmaEnd - kSmTma, "three packed blocks must fit the staging area");
+      if (tid == 0)
+        for (int pre = 0; pre < 2 && pre < nown; pre++)
+          tma_load_1d(bbuf + pre * kPackedBlock, G.Binv + (size_t)(c.rank + c.tsize * pre) * kPackedBlock, kBlockBytes, gbar + pre);
       for (int ib = 0; ib < nown; ib++) {
         const int k = c.rank + c.tsize * ib;
-        if (tid == 0 && ib + 1 < nown)
-          tma_load_1d(bbuf + ((ib + 1) & 1) * kBlockDim * kBlockDim, G.Binv + (size_t)(k + c.tsize) * kBlockDim * kBlockDim, kBlockBytes,
-                      gbar + ((ib + 1) & 1));
+        const int stg = ib % 3;
+        if (tid == 0 && ib + 2 < nown)
+          tma_load_1d(bbuf + ((ib + 2) % 3) * kPackedBlock, G.Binv + (size_t)(k + 2 * c.tsize) * kPackedBlock, kBlockBytes, gbar + (ib + 2) % 3);
         const double* rv = sR + (size_t)ib * kBlockDim;   // (ib = slot + kSlots * rd: the staging order of part A)
         const int np = min(kBlockPoses, G.N - k * kBlockPoses);
-        mbar_wait(gbar + (ib & 1), (c.gj_par >> (ib & 1)) & 1u);
-        c.gj_par ^= (1u << (ib & 1));
-        if (tid < kBlockDim) {
-          const double* B = bbuf + (ib & 1) * kBlockDim * kBlockDim + tid;
+        mbar_wait(gbar + stg, (c.gj_par >> stg) & 1u);
+        c.gj_par ^= (1u << stg);
+        if (tid < 4 * kBlockDim) {
+          // four threads per row of the symmetric block (interleaved columns, fixed-order combination by two shuffles):
+          // column part j < u reads element (j, u), row part j >= u reads element (u, j) of the packed upper triangle
+          const int u = tid >> 2, qq = tid & 3;
+          const double* cb = bbuf + stg * kPackedBlock;
           double zl = 0;
-#pragma unroll 8
-          for (int j = 0; j < kBlockDim; j++) zl += B[j * kBlockDim] * rv[j];
-          const int p = k * kBlockPoses + tid / 6;
-          if (p < G.N) {
-            G.z[(size_t)p * 6 + tid % 6] = zl;   // large graphs: only the owner reads z (update_direction)
-            dot += rv[tid] * zl;
+          for (int j = qq; j < u; j += 4) zl += cb[j * kBlockDim - (j * (j - 1)) / 2 + (u - j)] * rv[j];
+          const double* cu = cb + u * kBlockDim - (u * (u - 1)) / 2 - u;
+          for (int j = u + ((qq - u) & 3); j < kBlockDim; j += 4) zl += cu[j] * rv[j];
+          zl += __shfl_xor_sync(0xffffffffu, zl, 1);
+          zl += __shfl_xor_sync(0xffffffffu, zl, 2);
+          const int p = k * kBlockPoses + u / 6;
+          if (qq == 0 && p < G.N) {
+            G.z[(size_t)p * 6 + u % 6] = zl;   // large graphs: only the owner reads z (update_direction)
+            dot += rv[u] * zl;
           }
-        } else if (tid >= 128 && tid < 128 + 12) {
-          restrict_block(rv, 0, tid - 128, k, np, rc_new);
+        } else if (tid >= 4 * kBlockDim && tid < 4 * kBlockDim + 12) {
+          restrict_block(rv, 0, tid - 4 * kBlockDim, k, np, rc_new);
         }
         __syncthreads();   // the buffer may be refilled
       }
@@ -2072,9 +2083,11 @@ struct Phase {
           const double* cu = cb + u * kBlockDim - (u * (u - 1)) / 2 - u;
           for (int j = u; j < kBlockDim; j++) zl += cu[j] * rv[j];
         } else {
-          const double* B = G.Binv + (size_t)k * kBlockDim * kBlockDim + u;
-#pragma unroll 32
-          for (int j = 0; j < kBlockDim; j++) zl += ldc(B + (size_t)j * kBlockDim) * sA[slot * kBlockDim + j];
+          const double* cb = G.Binv + (size_t)k * kPackedBlock;   // packed upper triangle, straight from L2
+          const double* rv = sA + slot * kBlockDim;
+          for (int j = 0; j < u; j++) zl += ldc(cb + j * kBlockDim - (j * (j - 1)) / 2 + (u - j)) * rv[j];
+          const double* cu = cb + u * kBlockDim - (u * (u - 1)) / 2 - u;
+          for (int j = u; j < kBlockDim; j++) zl += ldc(cu + j) * rv[j];
         }
         put(c, &G.z[(size_t)p * 6 + row], zl);
         dot += rn * zl;
