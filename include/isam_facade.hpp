@@ -449,6 +449,9 @@ class Slam {
     q.max_iterations = p.max_iterations; q.lm_lambda0 = p.lm_lambda0; q.lm_lambda_factor = p.lm_lambda_factor;
     q.mod_update = p.mod_update; q.mod_batch = p.mod_batch; q.mod_solve = p.mod_solve;
     detail::check(pus_set_properties(_h, &q));
+    // Properties::force_numerical_jacobian (Properties.h:44-45): the reference's own numericalDiff scheme on the device instead
+    // of the closed-form blocks -- the mode in which a solve follows the reference's trajectory step for step
+    detail::check(pus_set_jacobian_mode(_h, p.force_numerical_jacobian ? 1 : 0));
   }
   void set_cost_function(cost_func_t f) { detail::check(pus_set_robust(_h, f.kind, f.b)); }   // Slam.cpp:212-214
   void add_node(Pose3d_Node* n) { n->_attach(_h); _nodes.push_back(n); }            // Slam.cpp:91-94

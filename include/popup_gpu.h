@@ -230,6 +230,16 @@ int pus_popup_fit_frames(int device, int n_frames, const int* seg_ptr, const flo
 int pus_refresh_plane_measurements(pus_handle h, int n_frames, const int* frame_pose, const int* seg_ptr,
                                    const float* segs, const float* invK, int n_map, const int* map_fid,
                                    const int* map_frame, const int* map_row, double* new_meas);
+/* Resident form of the same sweep (the reference re-pops EVERY past frame after EVERY solve, Mapping.cpp:590-607, while the
+ * frames' segment lists never change): pus_refresh_bind uploads the tables once (again whenever frames / factors are added);
+ * pus_refresh_run re-pops every bound frame from the device-resident pose estimates and stores the new measurements straight
+ * into the device factor store.  new_meas = NULL: nothing returns to the host -- the host mirrors (pus_get_measurement,
+ * FactorT::measurement()) are refreshed lazily on their next read or at the next layout rebuild; new_meas != NULL: [n_map][4]
+ * out, mirrors refreshed at once.  A structural edit between bind and run is fine as long as the bound frames / factors still
+ * exist (the layout-dependent tables are rebuilt by the run). */
+int pus_refresh_bind(pus_handle h, int n_frames, const int* frame_pose, const int* seg_ptr, const float* segs, const float* invK,
+                     int n_map, const int* map_fid, const int* map_frame, const int* map_row);
+int pus_refresh_run(pus_handle h, double* new_meas);
 /* Plane3d::project_to_plane (isam_plane3d.h:172-177) over point lists, as Mapper_mono::reproj_to_newplane
  * applies it to every stored polygon vertex (Mapping.cpp:609-632): pts_out[i] = float(project(double(pts_in[i])))
  * onto the current device-resident estimate of plane node plane_of_point[i]. */

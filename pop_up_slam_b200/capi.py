@@ -319,6 +319,23 @@ class GraphAPI:
                      invK.ctypes.data_as(c_float_p), len(map_fid), _ip(map_fid), _ip(map_frame), _ip(map_row), _dp(out)))
         return out
 
+    def refresh_bind(self, frame_pose, seg_ptr, segs, invK, map_fid, map_frame, map_row):
+        """pus_refresh_bind: keep the frames' segment lists / invK / factor map resident on the device."""
+        frame_pose, seg_ptr = _i32(frame_pose), _i32(seg_ptr)
+        segs = np.ascontiguousarray(segs, dtype=np.float32).reshape(-1, 4)
+        invK = np.ascontiguousarray(invK, dtype=np.float32).reshape(3, 3)
+        map_fid, map_frame, map_row = _i32(map_fid), _i32(map_frame), _i32(map_row)
+        self._n_map = len(map_fid)
+        self._chk(self._f("refresh_bind")(self.h, len(frame_pose), _ip(frame_pose), _ip(seg_ptr), segs.ctypes.data_as(c_float_p),
+                                          invK.ctypes.data_as(c_float_p), len(map_fid), _ip(map_fid), _ip(map_frame), _ip(map_row)))
+
+    def refresh_run(self, want_output=False):
+        """pus_refresh_run: re-pop every bound frame from the resident pose estimates; new measurements stay on the device unless
+        `want_output`."""
+        out = np.zeros((self._n_map, 4)) if want_output else None
+        self._chk(self._f("refresh_run")(self.h, _dp(out) if want_output else None))
+        return out
+
     def project_to_planes(self, plane_ids, pts):
         """Plane3d::project_to_plane of float points onto the current plane estimates (include/popup_gpu.h)."""
         plane_ids = _i32(plane_ids)

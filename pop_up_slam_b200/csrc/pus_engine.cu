@@ -72,6 +72,18 @@ struct Solver {
   bool values_dirty = false;             // host values changed since the last upload (pus_init_*): device copies are stale
   DevGraph* d_batch = nullptr;           // parameter blocks of a batched launch (grow-only)
   int d_batch_cap = 0;
+  // resident tables of pus_refresh_bind / pus_refresh_run (frames' ground segments, invK, factor <-> plane-row map)
+  struct RefreshTables {
+    bool bound = false;
+    int n_frames = 0, n_seg = 0, n_rows = 0, n_map = 0;
+    std::vector<int> frame_node, map_fid, mrow;   // host copies: pose node id per frame, factor id and plane row per map entry
+    uint64_t slot_topo = 0;                       // layout version the device slot / pose-index tables were built for
+    void* mem = nullptr; size_t bytes = 0;        // one allocation carved into the pointers below
+    int *d_fpose = nullptr, *d_ptr = nullptr, *d_rf = nullptr, *d_mrow = nullptr, *d_mslot = nullptr;
+    float *d_segs = nullptr, *d_K = nullptr, *d_T = nullptr, *d_ps = nullptr;
+    double* d_out = nullptr;
+  } rt;
+  bool meas_device_newer = false;        // pus_refresh_run(h, NULL) left newer pose-plane measurements on the device than in the host mirrors
   std::map<std::string, std::pair<double*, size_t>> named;  // debug access to double buffers
   DevGraph hd;
   DevGraph* d_graph = nullptr;
@@ -171,6 +183,21 @@ static int ensure_device(Solver* s) {
   return 0;
 }
 
+// pose-plane measurements refreshed on the device (pus_refresh_run without a host buffer) -> host factor store + compiled copy
+static int sync_measurements_to_host(Solver* s) {
+  if (!s->meas_device_newer) return 0;
+  s->meas_device_newer = false;
+  if (!s->uploaded || s->compiled_topo == 0) return 0;
+  Compiled& c = s->c;
+  if (!c.nslot) return 0;
+  CUDA_OK(cudaSetDevice(s->device));
+  CUDA_OK(cudaMemcpyAsync(c.pp_meas.data(), s->hd.pp_meas, c.pp_meas.size() * 8, cudaMemcpyDeviceToHost, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));
+  for (int e = 0; e < c.nslot; e++)
+    if (c.pp_fid[e] >= 0) std::memcpy(s->g.factors[c.pp_fid[e]].meas, &c.pp_meas[(size_t)e * 4], 4 * sizeof(double));
+  return 0;
+}
+
 // (re)build the HBM image of the graph.  Topology arrays are re-uploaded only after a structural edit;
 // vertex values always; measurements when pus_set_measurement touched them.
 static int upload(Solver* s) {
@@ -183,6 +210,7 @@ static int upload(Solver* s) {
     if (want != s->g.force_levels) { s->g.force_levels = want; s->g.topo_version++; }
   }
   const bool rebuild = (s->compiled_topo != s->g.topo_version) || !s->uploaded;
+  if ((rebuild || s->meas_dirty) && s->meas_device_newer && sync_measurements_to_host(s) < 0) return -1;   // (the layout is rebuilt from the host store)
   if (rebuild) {
     s->recycle_device();
     std::string err;
@@ -509,6 +537,7 @@ int pus_destroy(pus_handle h) {
   for (void* pp : s->span_peers) if (pp) cudaIpcCloseMemHandle(pp);
   s->free_device();
   if (s->d_batch) cudaFree(s->d_batch);
+  if (s->rt.mem) cudaFree(s->rt.mem);
   if (s->scratch) cudaFree(s->scratch);
   if (s->ev0) cudaEventDestroy(s->ev0);
   if (s->ev1) cudaEventDestroy(s->ev1);
@@ -608,6 +637,7 @@ int pus_set_measurement(pus_handle h, int fid, const double* m) {
   NEED(h);
   Solver* s = SV(h);
   if (!s->g.ok_factor(fid)) { g_err = "bad factor id"; return -1; }
+  if (sync_measurements_to_host(s) < 0) return -1;
   HFactor& f = s->g.factors[fid];
   if (f.dim == 3) { std::memcpy(f.meas, m, 4 * sizeof(double)); normalize4(f.meas); }
   else std::memcpy(f.meas, m, 6 * sizeof(double));
@@ -617,6 +647,7 @@ int pus_set_measurement(pus_handle h, int fid, const double* m) {
 int pus_get_measurement(pus_handle h, int fid, double* m) {
   NEED(h);
   if (!SV(h)->g.ok_factor(fid)) { g_err = "bad factor id"; return -1; }
+  if (sync_measurements_to_host(SV(h)) < 0) return -1;
   const HFactor& f = SV(h)->g.factors[fid];
   std::memcpy(m, f.meas, (f.dim == 3 ? 4 : 6) * sizeof(double)); return 0;
 }
@@ -907,6 +938,125 @@ int pus_refresh_plane_measurements(pus_handle h, int n_frames, const int* frame_
   return 0;
 }
 
+// ---- resident form: the frames' segment lists, invK and the factor map stay on the device between calls ----
+static int refresh_slots(Solver* s) {   // (re)build the layout-dependent tables: pose index per frame, edge slot per map entry
+  Solver::RefreshTables& t = s->rt;
+  const Compiled& c = s->c;
+  std::vector<int> fpose(t.n_frames), mslot(t.n_map);
+  for (int f = 0; f < t.n_frames; f++) {
+    if (!s->g.ok_node(t.frame_node[f], NODE_POSE)) { g_err = "pus_refresh_run: frame " + std::to_string(f) + " is no longer a pose node; bind again"; return -1; }
+    fpose[f] = c.node_idx[t.frame_node[f]];
+  }
+  if ((int)s->fid2slot.size() != (int)s->g.factors.size() || s->fid2slot_topo != s->compiled_topo) {
+    s->fid2slot.assign(s->g.factors.size(), -1);
+    for (int e = 0; e < c.nslot; e++) if (c.pp_fid[e] >= 0) s->fid2slot[c.pp_fid[e]] = e;
+    s->fid2slot_topo = s->compiled_topo;
+  }
+  for (int m = 0; m < t.n_map; m++) {
+    const int fid = t.map_fid[m];
+    if (!s->g.ok_factor(fid) || s->g.factors[fid].kind != F_POSE_PLANE || s->fid2slot[fid] < 0) {
+      g_err = "pus_refresh_run: map entry " + std::to_string(m) + " is no longer a pose-plane factor; bind again";
+      return -1;
+    }
+    mslot[m] = s->fid2slot[fid];
+  }
+  CUDA_OK(cudaMemcpyAsync(t.d_fpose, fpose.data(), sizeof(int) * t.n_frames, cudaMemcpyHostToDevice, s->stream));
+  if (t.n_map) CUDA_OK(cudaMemcpyAsync(t.d_mslot, mslot.data(), sizeof(int) * t.n_map, cudaMemcpyHostToDevice, s->stream));
+  CUDA_OK(cudaStreamSynchronize(s->stream));   // (the staging vectors go out of scope)
+  t.slot_topo = s->compiled_topo;
+  return 0;
+}
+
+int pus_refresh_bind(pus_handle h, int n_frames, const int* frame_pose, const int* seg_ptr, const float* segs, const float* invK,
+                     int n_map, const int* map_fid, const int* map_frame, const int* map_row) {
+  NEED(h);
+  Solver* s = SV(h);
+  Solver::RefreshTables& t = s->rt;
+  t.bound = false;
+  if (n_frames <= 0 || n_map < 0) { g_err = "pus_refresh_bind: nothing to bind"; return -1; }
+  if (ensure_device(s) < 0) return -1;
+  const int n_seg = seg_ptr[n_frames], n_rows = n_seg + n_frames;
+  std::vector<int> row_frame(n_rows);
+  t.frame_node.assign(frame_pose, frame_pose + n_frames);
+  t.map_fid.assign(map_fid, map_fid + n_map);
+  t.mrow.resize(n_map);
+  for (int f = 0; f < n_frames; f++) {
+    if (!s->g.ok_node(frame_pose[f], NODE_POSE)) { g_err = "frame " + std::to_string(f) + ": not a pose node"; return -1; }
+    if (seg_ptr[f + 1] < seg_ptr[f]) { g_err = "seg_ptr must be non-decreasing"; return -1; }
+    for (int r = seg_ptr[f] + f; r < seg_ptr[f + 1] + f + 1; r++) row_frame[r] = f;
+  }
+  for (int m = 0; m < n_map; m++) {
+    const int f = map_frame[m];
+    if (f < 0 || f >= n_frames) { g_err = "map_frame out of range"; return -1; }
+    const int ns = seg_ptr[f + 1] - seg_ptr[f];
+    if (ns <= 0 || map_row[m] < 0 || map_row[m] > ns) { g_err = "map_row out of range (frames without segments produce no planes)"; return -1; }
+    if (!s->g.ok_factor(map_fid[m]) || s->g.factors[map_fid[m]].kind != F_POSE_PLANE) { g_err = "map_fid is not a pose-plane factor"; return -1; }
+    t.mrow[m] = seg_ptr[f] + f + map_row[m];
+  }
+  auto al = [](size_t b) { return (b + 255) / 256 * 256; };
+  const size_t need = al(4 * (size_t)n_frames) + al(4 * (size_t)(n_frames + 1)) + al(4 * (size_t)n_rows) + 2 * al(4 * (size_t)std::max(n_map, 1)) +
+                      al(16 * (size_t)std::max(n_seg, 1)) + al(36) + al(64 * (size_t)n_frames) + al(16 * (size_t)n_rows) + al(32 * (size_t)std::max(n_map, 1));
+  CUDA_OK(cudaSetDevice(s->device));
+  if (need > t.bytes) {
+    if (t.mem) { cudaStreamSynchronize(s->stream); cudaFree(t.mem); t.mem = nullptr; t.bytes = 0; }
+    CUDA_OK(cudaMalloc(&t.mem, need + need / 2));
+    t.bytes = need + need / 2;
+  }
+  char* base = static_cast<char*>(t.mem);
+  size_t off = 0;
+  auto carve = [&](size_t b) { void* p = base + off; off += al(b); return p; };
+  t.d_fpose = (int*)carve(4 * (size_t)n_frames); t.d_ptr = (int*)carve(4 * (size_t)(n_frames + 1)); t.d_rf = (int*)carve(4 * (size_t)n_rows);
+  t.d_mrow = (int*)carve(4 * (size_t)std::max(n_map, 1)); t.d_mslot = (int*)carve(4 * (size_t)std::max(n_map, 1));
+  t.d_segs = (float*)carve(16 * (size_t)std::max(n_seg, 1)); t.d_K = (float*)carve(36); t.d_T = (float*)carve(64 * (size_t)n_frames);
+  t.d_ps = (float*)carve(16 * (size_t)n_rows); t.d_out = (double*)carve(32 * (size_t)std::max(n_map, 1));
+  cudaStream_t st = s->stream;
+  CUDA_OK(cudaMemcpyAsync(t.d_ptr, seg_ptr, 4 * (size_t)(n_frames + 1), cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(t.d_rf, row_frame.data(), 4 * (size_t)n_rows, cudaMemcpyHostToDevice, st));
+  if (n_seg) CUDA_OK(cudaMemcpyAsync(t.d_segs, segs, 16 * (size_t)n_seg, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemcpyAsync(t.d_K, invK, 36, cudaMemcpyHostToDevice, st));
+  if (n_map) CUDA_OK(cudaMemcpyAsync(t.d_mrow, t.mrow.data(), 4 * (size_t)n_map, cudaMemcpyHostToDevice, st));
+  CUDA_OK(cudaMemsetAsync(t.d_ps, 0, 16 * (size_t)n_rows, st));
+  CUDA_OK(cudaStreamSynchronize(st));
+  t.n_frames = n_frames; t.n_seg = n_seg; t.n_rows = n_rows; t.n_map = n_map;
+  t.slot_topo = 0;
+  t.bound = true;
+  return 0;
+}
+
+int pus_refresh_run(pus_handle h, double* new_meas) {
+  NEED(h);
+  Solver* s = SV(h);
+  Solver::RefreshTables& t = s->rt;
+  if (!t.bound) { g_err = "pus_refresh_run: call pus_refresh_bind first"; return -1; }
+  if (!s->uploaded || s->compiled_topo != s->g.topo_version || s->values_dirty || s->meas_dirty) {
+    if (upload(s) < 0) return -1;
+  } else if (ensure_device(s) < 0) {
+    return -1;
+  }
+  if (t.slot_topo != s->compiled_topo && refresh_slots(s) < 0) return -1;
+  CUDA_OK(cudaSetDevice(s->device));
+  cudaStream_t st = s->stream;
+  CUDA_OK(cudaEventRecord(s->ev0, st));
+  CUDA_OK(launch_refresh(st, t.n_frames, t.d_fpose, s->hd.pose_lin, t.d_ptr, t.d_rf, t.n_rows, t.d_segs, t.d_K, t.d_T, t.d_ps, t.n_map, t.d_mrow,
+                         t.d_mslot, const_cast<double*>(s->hd.pp_meas), t.d_out));
+  CUDA_OK(cudaEventRecord(s->ev1, st));
+  if (new_meas && t.n_map) {
+    CUDA_OK(cudaMemcpyAsync(new_meas, t.d_out, (size_t)t.n_map * 32, cudaMemcpyDeviceToHost, st));
+    CUDA_OK(cudaStreamSynchronize(st));
+    for (int m = 0; m < t.n_map; m++) {   // host mirrors: the factor store and the compiled copy
+      std::memcpy(s->g.factors[t.map_fid[m]].meas, new_meas + (size_t)m * 4, 4 * sizeof(double));
+      std::memcpy(&s->c.pp_meas[(size_t)s->fid2slot[t.map_fid[m]] * 4], new_meas + (size_t)m * 4, 4 * sizeof(double));
+    }
+  } else {
+    CUDA_OK(cudaEventSynchronize(s->ev1));
+    if (t.n_map) s->meas_device_newer = true;   // host mirrors are refreshed lazily (pus_get_measurement, next layout rebuild)
+  }
+  float ms = 0;
+  CUDA_OK(cudaEventElapsedTime(&ms, s->ev0, s->ev1));
+  s->stats.kernel_ms = ms; s->stats.gpu_launches = 3;
+  return 0;
+}
+
 int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point, const float* pts_in, float* pts_out) {
   NEED(h);
   Solver* s = SV(h);
@@ -939,6 +1089,7 @@ int pus_project_to_planes(pus_handle h, int n_points, const int* plane_of_point,
 int pus_save_graph(pus_handle h, const char* path, int precision) {
   NEED(h);
   Solver* s = SV(h);
+  if (sync_measurements_to_host(s) < 0) return -1;
   FILE* fp = std::fopen(path, "wb");
   if (!fp) { g_err = std::string("pus_save_graph: cannot open ") + path; return -1; }
   const int prec = precision > 0 ? precision : 6;

@@ -13,6 +13,15 @@
 using namespace isam;
 
 static int run(int argc, char** argv);
+// a diagonal covariance for either flavour of the facade's dense types (built-in, or Eigen with -DISAM_FACADE_USE_EIGEN: what
+// Mapping.cpp itself does at :64-67 -- MatrixXd::Zero + diagonal entries)
+static MatrixXd diag_matrix(const std::vector<double>& d) {
+  MatrixXd m((int)d.size(), (int)d.size());
+  for (size_t i = 0; i < d.size(); i++)
+    for (size_t j = 0; j < d.size(); j++) m((int)i, (int)j) = (i == j) ? d[i] : 0.0;
+  return m;
+}
+
 int main(int argc, char** argv) {
   try { return run(argc, argv); }
   catch (const std::exception& e) { fprintf(stderr, "facade_replay: %s\n", e.what()); return 1; }
@@ -39,8 +48,8 @@ static int run(int argc, char** argv) {
   if (fscanf(f, "%lf", &ground_sig) != 1) return 2;
   std::vector<double> pv(6);
   for (int i = 0; i < 6; i++) pv[i] = pose_sig[i] * pose_sig[i];
-  Covariance poseCov(MatrixXd::Diagonal(pv));
-  Covariance groundCov(MatrixXd::Diagonal({ground_sig * ground_sig, ground_sig * ground_sig, ground_sig * ground_sig}));
+  Covariance poseCov(diag_matrix(pv));
+  Covariance groundCov(diag_matrix({ground_sig * ground_sig, ground_sig * ground_sig, ground_sig * ground_sig}));
   for (int fr = 0; fr < n_frames; fr++) {
     double o[6];
     for (int i = 0; i < 6; i++) if (fscanf(f, "%lf", &o[i]) != 1) return 2;
@@ -69,7 +78,7 @@ static int run(int argc, char** argv) {
         planes[pl]->init(measure.transform_from(estimate_pose.oTw()));             // Mapping.cpp:497-499
         if (pl == ground) slam.add_factor(new Plane3d_Factor(planes[pl], Plane3d(Vector4d(0, 0, -1, 0)), groundCov));
       }
-      Covariance cov(MatrixXd::Diagonal({sig * sig, sig * sig, sig * sig}));
+      Covariance cov(diag_matrix({sig * sig, sig * sig, sig * sig}));
       slam.add_factor(new Pose3d_Plane3d_Factor(poseNode, planes[pl], measure, cov, false));
     }
     if (fr % 5 == 0) slam.batch_optimization(); else slam.update();                 // Mapping.cpp:550-554

@@ -14,12 +14,16 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 BIN = os.path.join(ROOT, "tests", "facade_replay")
 
 
-def build_replay():
+def build_replay(eigen=False):
+    """eigen=True: the -DISAM_FACADE_USE_EIGEN flavour of include/isam_facade.hpp (the one INTEGRATION.md tells a maintainer to
+    use), compiled against the Eigen API stand-in of oracle/ref_shim -- Eigen itself is not installed in the build container."""
     src = os.path.join(ROOT, "tests", "facade_replay.cpp")
     libdir = os.path.join(ROOT, "pop_up_slam_b200")
-    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall", "-o", BIN, src, "-L" + libdir, "-lpopup_gpu",
+    out = BIN + ("_eigen" if eigen else "")
+    extra = ["-DISAM_FACADE_USE_EIGEN", "-I" + os.path.join(ROOT, "oracle", "ref_shim")] if eigen else []
+    subprocess.check_call(["g++", "-std=c++17", "-O2", "-Wall"] + extra + ["-o", out, src, "-L" + libdir, "-lpopup_gpu",
                            "-Wl,-rpath," + libdir])
-    return BIN
+    return out
 
 
 def write_frames(g, path, sig_of_edge):
@@ -56,9 +60,28 @@ def test_facade_fails_loudly_without_gpu(tmp_path):
     assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
 
 
+def test_facade_eigen_flavour_compiles_and_fails_loudly_without_a_gpu(tmp_path):
+    """the ISAM_FACADE_USE_EIGEN branch builds (against the Eigen API stand-in) and, like the built-in flavour, has no CPU fallback"""
+    import ctypes
+    exe = build_replay(eigen=True)
+    try:
+        ctypes.CDLL("libcuda.so.1")
+        has_gpu = subprocess.run(["nvidia-smi", "-L"], capture_output=True).returncode == 0
+    except OSError:
+        has_gpu = False
+    if has_gpu:
+        pytest.skip("a GPU is present: covered by test_facade_replay_matches_oracle[eigen]")
+    g = gg.make_config(1, seed=0, sigma_mode="reference")
+    path = tmp_path / "frames.txt"
+    write_frames(g, path, (1.0 / g.pp_sqrtinf[:, 0]).tolist())
+    r = subprocess.run([exe, str(path)], capture_output=True, text=True)
+    assert r.returncode != 0 and "no CUDA device" in (r.stderr + r.stdout)
+
+
 @pytest.mark.gpu
-def test_facade_replay_matches_oracle(tmp_path):
-    build_replay()
+@pytest.mark.parametrize("eigen", [False, True], ids=["builtin", "eigen"])
+def test_facade_replay_matches_oracle(tmp_path, eigen):
+    BIN = build_replay(eigen)
     g = gg.make_config(2, seed=6, n_poses=30, n_planes=10, sigma_mode="reference")
     sig = (1.0 / g.pp_sqrtinf[:, 0])
     path = tmp_path / "frames.txt"

@@ -426,6 +426,50 @@ def test_popup_fit_matches_oracle():
             assert np.array_equal(a, b)   # float32, same operation order, no FMA contraction: bit-exact
 
 
+def test_resident_measurement_refresh_matches_one_shot_call():
+    """pus_refresh_bind / pus_refresh_run: the frames' segment tables stay on the device; a run without a host buffer leaves
+    the new measurements only in the device factor store (the next solve uses them), the host mirrors are refreshed lazily by
+    pus_get_measurement; a structural edit between bind and run only rebuilds the slot tables.  Same measurements, next solve
+    and estimates as the one-shot call (itself checked against the oracle below)."""
+    g = gg.make_config(2, seed=6, n_poses=90, n_planes=20)
+    rng = np.random.default_rng(12)
+    nf = g.n_poses
+    nseg = rng.integers(1, 6, size=nf)
+    seg_ptr = np.concatenate([[0], np.cumsum(nseg)]).astype(np.int32)
+    segs = np.stack([rng.uniform(0, 640, seg_ptr[-1]), rng.uniform(300, 480, seg_ptr[-1]),
+                     rng.uniform(0, 640, seg_ptr[-1]), rng.uniform(300, 480, seg_ptr[-1])], axis=1).astype(np.float32)
+    invK = np.linalg.inv(np.array([[535.4, 0, 320.1], [0, 539.2, 247.6], [0, 0, 1.0]])).astype(np.float32)
+    order = np.argsort(g.pp_pose, kind="stable")
+    mf = [int(g.pp_pose[e]) for e in order]
+    mr = [int(rng.integers(0, nseg[f] + 1)) for f in mf]
+    res = []
+    for resident in (False, True):
+        api = GpuGraphAPI()
+        info = gg.build_bulk(api, g)
+        gg.configure(api, g)
+        api.batch_optimize()
+        fids = info["pp_fids"][order]
+        if resident:
+            api.refresh_bind(info["pose_ids"], seg_ptr, segs, invK, fids, mf, mr)
+            extra = api.add_pose_plane(int(info["pose_ids"][3]), int(info["plane_ids"][1]), g.pp_meas[0], g.pp_sqrtinf[0])   # edit after bind
+            api.remove_factor(extra)
+            api.refresh_run()                              # device only
+            it2 = api.batch_optimize()                     # uses the refreshed measurements
+            new = np.array([api.get_measurement(int(f))[:4] for f in fids])   # lazy mirror refresh
+            again = api.refresh_run(want_output=True)      # second run, now from the re-optimised poses, with output
+            assert np.array_equal(again, np.array([api.get_measurement(int(f))[:4] for f in fids]))
+        else:
+            extra = api.add_pose_plane(int(info["pose_ids"][3]), int(info["plane_ids"][1]), g.pp_meas[0], g.pp_sqrtinf[0])
+            api.remove_factor(extra)
+            new = api.refresh_plane_measurements(info["pose_ids"], seg_ptr, segs, invK, fids, mf, mr)
+            it2 = api.batch_optimize()
+        res.append((new, it2, api.chi2(), api.get_poses(info["pose_ids"])))
+    (n0, i0, c0, P0), (n1, i1, c1, P1) = res
+    assert np.array_equal(n0, n1)
+    assert i0 == i1 and abs(c0 - c1) <= 1e-12 * abs(c0)
+    assert np.array_equal(P0, P1)
+
+
 def test_measurement_refresh_and_reprojection_match_oracle():
     """SURVEY 8f.1: Mapper_mono::update_plane_measurement / reproj_to_newplane on the device-resident estimates.
     After a solve every frame re-pops its planes with its latest pose and the kept observations become the new

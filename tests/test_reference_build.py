@@ -386,3 +386,88 @@ def test_gpu_against_the_reference_library_directly(cfg, seed):
     assert np.array_equal(gpu.trace()["accepted"], ref.trace()["accepted"])
     assert abs(gpu.chi2() - ref.chi2()) <= 1e-4 * ref.chi2()
     _compare_estimates(gpu, ref, ig, ir, 1e-4)
+
+
+def _loopclose_scenario(api, g, n_dup=4):
+    """A graph in which `n_dup` walls were re-detected as NEW landmarks in the second half of the trajectory (what happens
+    before a loop closure), built in processFrame's order; returns the ids and, per duplicate, its factor ids."""
+    rng = np.random.default_rng(7)
+    n, m = g.n_poses, g.n_planes
+    counts = np.bincount(g.pp_plane, minlength=m)
+    cand = [k for k in np.argsort(-counts) if k != g.ground_plane][:n_dup]
+    pose_ids = api.add_poses(g.poses_init)
+    plane_ids = api.add_planes(g.planes_init)
+    dup_ids = {int(k): api.add_plane(g.planes_init[k] + 0) for k in cand}
+    api.add_pose_prior(pose_ids[g.prior_pose], g.prior_meas, g.prior_sqrtinf)
+    api.add_odometry_bulk(pose_ids[g.odo_i], pose_ids[g.odo_j], g.odo_meas, g.odo_sqrtinf)
+    api.add_plane_prior(plane_ids[g.ground_plane], g.ground_meas, g.ground_sqrtinf)
+    dup_facs = {k: [] for k in dup_ids}
+    late = set()     # the later half of each candidate wall's observations go to its duplicate
+    for k in dup_ids:
+        es = np.nonzero(g.pp_plane == k)[0]
+        es = es[np.argsort(g.pp_pose[es], kind="stable")]
+        late.update(int(e) for e in es[len(es) // 2:])
+    fids = []
+    for e in range(g.n_pose_plane):
+        p, k = int(g.pp_pose[e]), int(g.pp_plane[e])
+        target = dup_ids[k] if e in late else plane_ids[k]
+        f = api.add_pose_plane(pose_ids[p], target, g.pp_meas[e], g.pp_sqrtinf[e])
+        fids.append(f)
+        if e in late:
+            dup_facs[k].append((f, e))
+    assert all(len(v) > 5 for v in dup_facs.values())
+    return dict(pose_ids=pose_ids, plane_ids=plane_ids, dup_ids=dup_ids, dup_facs=dup_facs)
+
+
+def _loopclose_merge(api, g, ids):
+    """Mapper_mono::loopclose_merge (Mapping.cpp:659-700), call for call: for every factor of the duplicate landmark a new
+    Pose3d_Plane3d_Factor on the matched landmark with the old measurement and noise is added, then the old one removed;
+    afterwards the duplicate plane vertex is removed; processFrame then runs batch_optimization() (loop_success)."""
+    for k, dup in ids["dup_ids"].items():
+        for f, e in ids["dup_facs"][k]:
+            api.add_pose_plane(ids["pose_ids"][int(g.pp_pose[e])], ids["plane_ids"][k], api.get_measurement(f, 4), g.pp_sqrtinf[e])
+            api.remove_factor(f)
+    for k, dup in ids["dup_ids"].items():
+        api.remove_node(dup)
+    return api.batch_optimize()
+
+
+def test_loopclose_merge_replay_matches_the_reference():
+    """SURVEY 8(f).2: the exact edit sequence of Mapper_mono::loopclose_merge replayed on the reference optimiser and on
+    the oracle: optimise with duplicated landmarks, merge, optimise again."""
+    g = gg.make_config(2, seed=5, n_poses=160, n_planes=30)
+    ref, orc = R.RefAPI(), OracleAPI()
+    orc.set_jacobian_mode(0)
+    out = []
+    for api in (ref, orc):
+        ids = _loopclose_scenario(api, g)
+        gg.configure(api, g)
+        it0 = api.batch_optimize()
+        c0 = api.chi2()
+        it1 = _loopclose_merge(api, g, ids)
+        out.append((ids, it0, c0, it1, api.chi2(), api.num_nodes(), api.num_factors()))
+    (ir, a0, c0r, a1, c1r, nnr, nfr), (io, b0, c0o, b1, c1o, nno, nfo) = out
+    assert (a0, a1, nnr, nfr) == (b0, b1, nno, nfo)
+    assert abs(c0r - c0o) <= 1e-9 * c0o and abs(c1r - c1o) <= 1e-9 * c1o
+    _compare_estimates(ref, orc, ir, io, 1e-8)
+
+
+@pytest.mark.gpu
+def test_gpu_loopclose_merge_replay_matches_the_reference():
+    """the same replay through the C-ABI of the CUDA library against the reference optimiser (tombstoned factors / node,
+    layout recompiled on the next solve, ids stable)."""
+    from pop_up_slam_b200.capi import GpuGraphAPI
+    g = gg.make_config(2, seed=5, n_poses=160, n_planes=30)
+    gpu, ref = GpuGraphAPI(), R.RefAPI()
+    out = []
+    for api in (gpu, ref):
+        ids = _loopclose_scenario(api, g)
+        gg.configure(api, g)
+        it0 = api.batch_optimize()
+        c0 = api.chi2()
+        it1 = _loopclose_merge(api, g, ids)
+        out.append((ids, it0, c0, it1, api.chi2(), api.num_nodes(), api.num_factors()))
+    (ig, a0, c0g, a1, c1g, nng, nfg), (ir, b0, c0r, b1, c1r, nnr, nfr) = out
+    assert (a0, a1, nng, nfg) == (b0, b1, nnr, nfr)
+    assert abs(c0g - c0r) <= 1e-4 * c0r and abs(c1g - c1r) <= 1e-4 * c1r
+    _compare_estimates(gpu, ref, ig, ir, 1e-4)
