@@ -1499,7 +1499,8 @@ struct Phase {
   // -------- PCG: owner part of the direction update p_new = z + beta p_old --------
   __device__ void update_direction(int cur, double beta) {
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
-    for (int rd = 0; rd < rounds(); rd++) {
+    const int nrounds = rounds();
+    for (int rd = 0; rd < nrounds; rd++) {
       int k = c.rank + c.tsize * (slot + kSlots * rd);
       int p = k * kBlockPoses + u / 6;
       if (slot < kSlots && k < G.nblk && p < G.N) {
@@ -1524,20 +1525,21 @@ struct Phase {
     double* tbuf = reinterpret_cast<double*>(c.smem + kSmTma) + (tid >> 5) * 2 * kWStride;  // TMA staging (large graphs)
     unsigned long long* tbar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + (tid >> 5) * 2;
     double dot = 0;
+    const int nrounds = rounds();
     // plane-group record of this thread for the coming round (static data, read one round ahead)
     int g0N = 0, ngN = 0;
     int4 giN = make_int4(0, 0, 0, 0);
     auto next_groups = [&](int rd) {
       const int k = c.rank + c.tsize * (slot + kSlots * rd);
       g0N = 0; ngN = 0;
-      if (rd < rounds() && slot < kSlots && k < G.nblk) {
+      if (rd < nrounds && slot < kSlots && k < G.nblk) {
         g0N = G.blk_grp_ptr[k];
         ngN = G.blk_grp_ptr[k + 1] - g0N;
         if (u < ngN) giN = *reinterpret_cast<const int4*>(G.grp_info + (size_t)(g0N + u) * 4);
       }
     };
     next_groups(0);
-    for (int rd = 0; rd < rounds(); rd++) {
+    for (int rd = 0; rd < nrounds; rd++) {
       const int k = c.rank + c.tsize * (slot + kSlots * rd);
       const bool live = (slot < kSlots) && (k < G.nblk);
       const int p = k * kBlockPoses + u / 6, row = u % 6;
@@ -1952,18 +1954,32 @@ struct Phase {
         for (int i = warp_team(); i < ldm; i += nw) {
           const double* arow = Ai + ac_index(G.ldmc, i, 0);
           double acc = 0;
-          int j = lane;
-          for (; j + 32 * 15 < ldm; j += 32 * 16) {   // 16 loads per lane in flight
-            double av[16];
+          // 128-bit loads, a lane owns column pairs (2 lane + 64 t): a 1 884-wide row is two batches of 16 loads in flight
+          // (pairs never straddle a 128-column tile: tile rows are 16-byte aligned, stride 132)
+          int j = 2 * lane;
+          for (; j + 64 * 15 < ldm; j += 64 * 16) {
+            double2 av[16];
   #pragma unroll
             for (int t = 0; t < 16; t++) {
-              const int jj = j + 32 * t;
-              av[t] = ldc(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk));
+              const int jj = j + 64 * t;
+              av[t] = __ldcg(reinterpret_cast<const double2*>(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk)));
             }
   #pragma unroll
-            for (int t = 0; t < 16; t++) acc += av[t] * src[j + 32 * t];
+            for (int t = 0; t < 16; t++) acc += av[t].x * src[j + 64 * t] + av[t].y * src[j + 64 * t + 1];
           }
-          for (; j < ldm; j += 32) acc += ldc(arow + (size_t)(j / kGjChunk) * kGjTile + (j % kGjChunk)) * src[j];
+          {
+            double2 av[16];
+  #pragma unroll
+            for (int t = 0; t < 16; t++) {
+              const int jj = j + 64 * t;
+              av[t] = (jj < ldm) ? __ldcg(reinterpret_cast<const double2*>(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk))) : make_double2(0.0, 0.0);
+            }
+  #pragma unroll
+            for (int t = 0; t < 16; t++) {
+              const int jj = j + 64 * t;
+              if (jj < ldm) acc += av[t].x * src[jj] + av[t].y * src[jj + 1];   // (ldm = 6 nc is even)
+            }
+          }
           acc = warp_sum(acc);
           if (lane == 0) { put(c, &G.zc[i], acc); dot += src[i] * acc; }
         }

@@ -201,3 +201,21 @@ def test_three_level_preconditioner_pieces():
     got = np.concatenate([gpu.debug_fetch("x", 6 * N), gpu.debug_fetch("dl", 3 * g.n_planes)])
     assert np.linalg.norm(got - ref) / np.linalg.norm(ref) < 1e-7
     print("three-level PCG iterations on the 610-pose corridor:", gpu.stats()["pcg_iterations"])
+
+
+def test_coarse_inverse_with_a_heavy_plane():
+    """A_c^-1 once the ground plane touches more than 16 coarse nodes (420 poses) and enters the Galerkin operator as a
+    dense rank-3 update: against numpy."""
+    g = small_graph(seed=5, n_poses=420, n_planes=52)
+    gpu, orc, ig, io = make_pair(g)
+    N = g.n_poses
+    lam = 1e-3
+    A, b, S = schur_reference(orc, g, lam)
+    gpu.upload()
+    gpu.debug_run_stage(1, lam)
+    P, nc = hat_matrix(N, 16)
+    Ac = P.T @ S @ P
+    ncp = (nc + 7) // 8 * 8
+    Acinv = gpu.debug_fetch("Acinv", 36 * ncp * ncp).reshape(6 * ncp, 6 * ncp)
+    assert relerr(Acinv[:6 * nc, :6 * nc], np.linalg.inv(Ac)) < 1e-7
+    assert np.allclose(Acinv[6 * nc:, 6 * nc:], np.eye(6 * (ncp - nc))) and np.all(Acinv[:6 * nc, 6 * nc:] == 0)
