@@ -21,9 +21,10 @@ __device__ int schur_setup(Phase& ph, Ctx& c, double lambda, Timer& ft, bool reb
   ph.plane_inverse(lambda);
   team_barrier(c);
   ft.lap(8);
-  if (!rebuild) return acinv_prev;
+  if (!rebuild && !ph.G.prm.blocks_always) return acinv_prev;
   ph.build_blocks(lambda);
   ft.lap(9);
+  if (!rebuild) { team_barrier(c); return acinv_prev; }   // level 1 refreshed for this linearisation, coarse level kept
   ph.coarse_wc();
   team_barrier(c);
   ft.lap(10);

@@ -326,7 +326,11 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
   p.robust_kind = s->robust_kind; p.robust_b = s->robust_b; p.jac_numeric = s->jac_numeric;
   p.pcg_tol = s->opt.pcg_rel_tol; p.pcg_max_iter = s->opt.pcg_max_iter;
   p.prec_refresh = s->opt.reserved[0] == 1 ? 0 : 1;
-  p.refresh_pct = s->opt.reserved[3] > 0 ? s->opt.reserved[3] : 200;   // rebuild when its > pct% of the post-build count + add
+  p.blocks_always = s->opt.reserved[0] == 2 ? 1 : 0;
+  // rebuild when its > pct% of the post-build count + add.  The dense coarse inverse goes stale mostly through lambda (four
+  // rejected steps in a row move it from 1e-6 to 1e-2): 130 % is the measured optimum on config 3 (58.2 vs 60.1 ms at 200 %),
+  // the three-level set-up of large graphs is dearer per build and prefers 200 % (config 5: 912 vs 947 ms)
+  p.refresh_pct = s->opt.reserved[3] > 0 ? s->opt.reserved[3] : (s->c.levels == 3 ? 200 : 130);
   p.refresh_add = 8;
   p.fine_timers = (s->opt.reserved[2] & 1) ? 1 : 0;     // reserved[2] bit 0: sub-phase timers inside the PCG phases
   p.tma_mode = (s->opt.reserved[2] & 2) ? 1 : ((s->opt.reserved[2] & 4) ? 2 : 0);  // bit 1: always stage tiles by TMA, bit 2: never

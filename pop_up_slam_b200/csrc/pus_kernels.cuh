@@ -46,6 +46,7 @@ struct LmParams {
   int fine_timers;   // 1: sub-phase timers (perturbs the run slightly)
   int refresh_pct, refresh_add;  // lazy preconditioner refresh threshold
   int tma_mode;      // 0: TMA-staged W/Wt tiles when a warp owns several tiles (large graphs), 1: always, 2: never
+  int blocks_always; // 1: the dense 16-pose blocks (level 1) are rebuilt for every linear solve, only the coarse level(s) lazily
   int jac_numeric;   // 1: reference-Jacobian mode (central differences, numericalDiff.cpp:41-87) instead of the closed forms
 };
 
