@@ -194,6 +194,27 @@ def test_large_graph_streaming_path():
     assert gpu.stats()["grid_ctas"] >= 120
 
 
+@pytest.mark.slow
+def test_config5_full_size_matches_oracle():
+    """BASELINE config 5 at FULL size (50 000 poses / 5 000 planes / 1 000 000 + 50 000 edges; three-level preconditioner,
+    bulk-copy data path, 148 CTAs) against the closed-form oracle on the same graph: 2 LM iterations (the CPU side takes about a
+    minute), same accept sequence, chi2 to 1e-6, estimates to 1e-4."""
+    g = gg.make_config(5, seed=0, max_iterations=2)
+    gpu, orc = GpuGraphAPI(), OracleAPI()
+    orc.set_jacobian_mode(1)
+    orc.set_reuse_ordering(1)
+    ig, io = gg.build_bulk(gpu, g), gg.build_bulk(orc, g)
+    gg.configure(gpu, g)
+    gg.configure(orc, g)
+    assert gpu.batch_optimize() == orc.batch_optimize()
+    st = gpu.stats()
+    tg, to = gpu.trace(), orc.trace()
+    assert np.array_equal(tg["accepted"], to["accepted"])
+    assert np.allclose(tg["chi2_new"], to["chi2_new"], rtol=1e-6)
+    compare(gpu, orc, ig, io)
+    assert st["grid_ctas"] == 148 and gpu.debug_fetch("dims", 18)[14] == 3
+
+
 @pytest.mark.parametrize("cfg,world,kw", [(2, 2, {}), (2, 3, {}), (3, 2, dict(n_poses=600, n_planes=60, max_iterations=8)),
                                           (3, 2, dict(n_poses=700, n_planes=70, max_iterations=6, force_large_path=True)),
                                           (3, 2, dict(n_poses=700, n_planes=70, max_iterations=6, three_level=True)),
