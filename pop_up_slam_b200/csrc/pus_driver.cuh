@@ -4,24 +4,28 @@
 // device: LM / GN driver
 // ---------------------------------------------------------------------------------------------
 __device__ void linearize(Phase& ph, Ctx& c) {
+  if (ph.ft) ph.ft->sync();
   ph.lin_pose_plane();
+  ph.lap2(6);
   ph.lin_other();
   team_barrier(c);
+  ph.lap2(22);
   ph.assemble();
   team_barrier(c);
+  ph.lap2(23);
 }
 
 // Schur complement set-up for a damping value; returns the buffer index of A_c^-1
 // Schur complement set-up for a damping value.  Hll^-1 (part of the operator) is always rebuilt; the two-level
 // preconditioner (dense diagonal blocks + coarse Galerkin inverse) only when `rebuild` -- a stale
 // preconditioner changes the PCG iteration count, never the solution.  Returns the buffer index of A_c^-1.
-__device__ __forceinline__ bool G_levels3(const Phase& ph) { return ph.G.levels == 3; }
+__device__ __forceinline__ bool G_levels3(const Phase&) { return G.levels == 3; }
 __device__ int schur_setup(Phase& ph, Ctx& c, double lambda, Timer& ft, bool rebuild, int acinv_prev) {
   ft.sync();
   ph.plane_inverse(lambda);
   team_barrier(c);
   ft.lap(8);
-  if (!rebuild && !ph.G.prm.blocks_always) return acinv_prev;
+  if (!rebuild && !G.prm.blocks_always) return acinv_prev;
   ph.build_blocks(lambda);
   ft.lap(9);
   if (!rebuild) { team_barrier(c); return acinv_prev; }   // level 1 refreshed for this linearisation, coarse level kept
@@ -46,10 +50,11 @@ __device__ __forceinline__ void span_view(Ctx& c, bool global) {
   else { c.rank = c.lrank; c.tsize = c.ltsize; c.mirror = 0; }
 }
 
-__device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambda, int acinv, int* its, Timer& ft, bool warm) {
+__device__ double schur_solve(Phase& ph, Ctx& c, double lambda, int acinv, int* its, Timer& ft, bool warm) {
   // spanning solve: the PCG phases are split over the CTAs of all ranks (every rank keeps full copies of the vectors)
   span_view(c, true);
-  if (!c.use_tma) {   // (large graphs use that shared memory for the TMA staging buffers instead)
+  const bool resident = G.prm.resident && !c.use_tma && !c.mirror;   // block-resident loop (pcg_resident): loads its own caches
+  if (!c.use_tma && !resident) {   // (large graphs use that shared memory for the TMA staging buffers instead)
     ph.cache_blocks();
     c.smem_cache_ok = 1;
   }
@@ -77,7 +82,9 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
     rz = v[0];
     if (!(rz > tol2 * rz0)) done = true;
   }
-  if (rz0 > 0.0 && !done) {
+  if (rz0 > 0.0 && !done && resident) {
+    it = ph.pcg_resident(lambda, acinv, rcb, rz0, rz, tol2, ft);
+  } else if (rz0 > 0.0 && !done) {
     while (it < G.prm.pcg_max_iter) {
       ft.sync();
       ph.update_direction(cur, beta);
@@ -119,12 +126,12 @@ __device__ double schur_solve(Phase& ph, Ctx& c, const DevGraph& G, double lambd
   return sqrt(v[0]);
 }
 
-__device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
-  Phase ph(G, c);
+__device__ void run_graph_impl(Ctx& c) {
+  Phase ph(c);
   const LmParams& P = G.prm;
   const bool lead = (c.rank == 0 && threadIdx.x == 0);
   LmResult* res = G.res;
-  Timer tm(lead, c.smem);
+  Timer tm(lead);
   Timer& ft = tm;
   ph.ft = (P.fine_timers ? &tm : nullptr);
   if (lead) {
@@ -172,7 +179,7 @@ __device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
       if (lead) res->status = acinv;
       if (P.debug_stage >= 2) {
         int its = 0;
-        double dn = schur_solve(ph, c, G, P.debug_lambda, acinv, &its, ft, false);
+        double dn = schur_solve(ph, c, P.debug_lambda, acinv, &its, ft, false);
         if (lead) { res->pcg_iters = its; res->chi2_final = dn; }
       }
     }
@@ -194,7 +201,7 @@ __device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
   int acinv = schur_setup(ph, c, lambda, ft, true, 0);
   int prec_builds = 1;
   tm.lap(1);
-  double dnorm = schur_solve(ph, c, G, lambda, acinv, &its, ft, false);
+  double dnorm = schur_solve(ph, c, lambda, acinv, &its, ft, false);
   pcg_total += its;
   int its_ref = its;  // PCG iterations right after the last preconditioner build
   tm.lap(2);
@@ -248,7 +255,7 @@ __device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
         const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref * P.refresh_pct / 100 + P.refresh_add);
         acinv = schur_setup(ph, c, lambda, ft, rebuild, acinv);
         tm.lap(1);
-        dnorm = schur_solve(ph, c, G, lambda, acinv, &its, ft, rejected && P.warm_start);
+        dnorm = schur_solve(ph, c, lambda, acinv, &its, ft, rejected && P.warm_start);
         if (rebuild) { its_ref = its; prec_builds++; }
       }
       last_pcg = its;
@@ -283,7 +290,7 @@ __device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
         const bool rebuild = (P.prec_refresh == 0) || (last_pcg > its_ref * P.refresh_pct / 100 + P.refresh_add);
         acinv = schur_setup(ph, c, 0.0, ft, rebuild, acinv);
         tm.lap(1);
-        dnorm = schur_solve(ph, c, G, 0.0, acinv, &its, ft, false);
+        dnorm = schur_solve(ph, c, 0.0, acinv, &its, ft, false);
         if (rebuild) { its_ref = its; prec_builds++; }
       }
       last_pcg = its;
@@ -303,9 +310,9 @@ __device__ void run_graph_impl(const DevGraph& G, Ctx& c) {
 
 // spanning solves keep the cross-rank barrier count across launches (every rank executes the same number of global
 // barriers per solve, so the counters are never reset while peers may already be running)
-__device__ void run_graph(const DevGraph& G, Ctx& c) {
+__device__ void run_graph(Ctx& c) {
   if (G.span_w > 1 && threadIdx.x == 0) c.gbar_target = __ldcg(G.gbar + 1);
-  run_graph_impl(G, c);
+  run_graph_impl(c);
   if (G.span_w > 1) {
     __syncthreads();
     if (threadIdx.x == 0) G.gbar[1] = c.gbar_target;
@@ -313,8 +320,7 @@ __device__ void run_graph(const DevGraph& G, Ctx& c) {
 }
 
 __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs, int n_graphs, int team_ctas, unsigned* bars) {
-  extern __shared__ __align__(128) unsigned char smem[];
-  __shared__ DevGraph sG;
+  unsigned char* const smem = g_smem;
   const int n_teams = gridDim.x / team_ctas;
   const int team = blockIdx.x / team_ctas;
   if (team >= n_teams) return;
@@ -325,11 +331,13 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
   c.bar_target = 0;
   c.red_slot = 0;
   c.smem_cache_ok = 0;
-  c.smem = smem;
+  c.smem = g_smem;
   c.use_tma = 0;
   c.tma_par = 0;
   c.gj_par = 0;
   c.span_w = 1; c.span_r = 0; c.mirror = 0; c.gbar = nullptr; c.gbar_target = 0;
+  c.rflag = reinterpret_cast<unsigned long long*>(bars + 8192) + (size_t)team * team_ctas * 4;
+  c.red_seq = 0;
   if (threadIdx.x == 0) {
     unsigned long long* gbar = reinterpret_cast<unsigned long long*>(smem + kSmGjBar);
     mbar_init(gbar, 1);
@@ -346,10 +354,12 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
   for (int g = team; g < n_graphs; g += n_teams) {
     __syncthreads();
     const int* src = reinterpret_cast<const int*>(graphs + g);
-    int* dst = reinterpret_cast<int*>(&sG);
+    int* dst = reinterpret_cast<int*>(&g_sG);
     for (int i = threadIdx.x; i < (int)(sizeof(DevGraph) / sizeof(int)); i += kThreads) dst[i] = src[i];
     __syncthreads();
-    run_graph(sG, c);
+    run_graph(c);
   }
 }
 
+
+#undef G

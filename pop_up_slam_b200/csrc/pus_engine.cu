@@ -230,7 +230,8 @@ static int upload(Solver* s) {
     d.n_heavy = c.n_heavy; d.n_huge = c.n_huge;
     UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pnbr); UP(pf_meas); UP(pf_sinf);
     UP(lp_plane); UP(linc_ptr); UP(linc); UP(lp_meas); UP(lp_sinf);
-    UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple); UP(grp_info);
+    UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple); UP(grp_info); UP(grp_info2);
+    d.res_nt = c.res_nt; d.res_ng = c.res_ng; d.res_np = c.res_np;
     UP(ce_ptr); UP(ce_node); UP(ce_plane); UP(ce_lo); UP(ce_hi); UP(n2ce_ptr); UP(n2ce);
     UP(hv_plane); UP(lp_ptr); UP(lp_cea); UP(lp_ceb); UP(fp_ptr); UP(fp_f);
     d.n_hv = c.n_hv;
@@ -244,7 +245,7 @@ static int upload(Solver* s) {
     AL(W, T * kWStride, "Wtiles"); AL(Wt, TL * kWStride, "Wttiles"); AL(JP, E * 21, "JP"); AL(JL, E * 12, "JL");
     AL(PF, (size_t)c.Epf * 120, "PF"); AL(LP, (size_t)c.Elp * 12, "LP");
     AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
-    AL(ypart, 8, "ypart");
+    AL(ypart, 8, "ypart"); AL(upartb, (size_t)std::max(1, c.ngrp) * 3, "upartb");
     AL(Binv, (size_t)c.nblk * kPackedBlock, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc"); AL(Yc, (size_t)c.nce * 18, "Yc");
     AL(Ac[0], ac_doubles(6 * c.nc_pad), "Ac0"); AL(Ac[1], ac_doubles(6 * c.nc_pad), "Ac1");
     AL(Wc2, (size_t)c.nce2 * 18, "Wc2"); AL(Yc2, (size_t)c.nce2 * 18, "Yc2"); AL(D2inv, (size_t)c.ng2 * kBlockDim * kBlockDim, "D2inv");
@@ -332,7 +333,7 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
   // the three-level set-up of large graphs is dearer per build and prefers 200 % (config 5: 912 vs 947 ms)
   p.refresh_pct = s->opt.reserved[3] > 0 ? s->opt.reserved[3] : (s->c.levels == 3 ? 200 : 130);
   p.refresh_add = 8;
-  p.fine_timers = (s->opt.reserved[2] & 1) ? 1 : 0;     // reserved[2] bit 0: sub-phase timers inside the PCG phases
+  p.fine_timers = (s->opt.reserved[2] & 64) ? 2 : ((s->opt.reserved[2] & 1) ? 1 : 0);   // bit 6: sub-phases of linearize instead     // reserved[2] bit 0: sub-phase timers inside the PCG phases
   p.tma_mode = (s->opt.reserved[2] & 2) ? 1 : ((s->opt.reserved[2] & 4) ? 2 : 0);  // bit 1: always stage tiles by TMA, bit 2: never
   p.warm_start = s->opt.reserved[1] == 1 ? 0 : 1;      // reserved[1] = 1: never warm-start PCG after a rejected step  // reserved[0] = 1: rebuild the preconditioner every solve
   p.mode = mode; p.debug_stage = debug_stage; p.debug_lambda = debug_lambda; p.restore_init = restore_init;
@@ -383,6 +384,15 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
   std::vector<DevGraph> hg(n);
   for (int i = 0; i < n; i++) {
     fill_params(ss[i], ss[i]->hd.prm, mode, restore_init, debug_stage, debug_lambda);
+    {
+      // block-resident PCG loop: two levels with one hat node per pose block, every CTA's owned blocks in one round, and the
+      // per-CTA layout (W tiles + packed preconditioner block + records per owned block) within the shared memory of an SM
+      const Compiled& cc = ss[i]->c;
+      const int nown = (cc.nblk + team - 1) / team;
+      const bool fits = cc.levels == 2 && cc.SP == kBlockPoses && nown >= 1 && nown <= kSlots && cc.res_ng <= 511 && cc.res_np <= 8191 &&
+                        res_layout(cc.res_nt, cc.res_ng, cc.res_np, 6 * cc.nc, nown).total <= kSmemBytes;
+      ss[i]->hd.prm.resident = (fits && !(ss[i]->opt.reserved[2] & 32) && ss[i]->hd.span_w <= 1) ? 1 : 0;   // reserved[2] bit 5: off
+    }
     hg[i] = ss[i]->hd;
   }
   DevGraph* d_graphs = s0->d_graph;

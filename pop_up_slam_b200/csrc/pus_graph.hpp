@@ -197,6 +197,11 @@ struct Compiled {
   std::vector<double> lp_meas, lp_sinf;
   // dense-block groups: per pose block, its edges grouped by plane
   std::vector<int> blk_grp_ptr, grp_plane, grp_mem_ptr, grp_mem, blk_simple, grp_info;
+  // block-resident PCG (small / medium graphs): the plane exchange is per (pose block, plane) instead of per plane-major tile
+  // run -- grp_info2 = {plane, first slot of the plane's per-block partial sums, their number, this group's own slot};
+  // res_* = largest tile / group / (tile, pose)-run count of any pose block (uniform shared-memory strides)
+  std::vector<int> grp_info2;
+  int res_nt = 0, res_ng = 0, res_np = 0;
   // coarse (hat) space: (plane, coarse node) pairs
   std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
   std::vector<int> hv_plane, lp_ptr, lp_cea, lp_ceb, fp_ptr, fp_f;   // coarse assembly: heavy planes, per node-pair lists
@@ -440,6 +445,28 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     c.grp_info[(size_t)g * 4] = l;
     c.grp_info[(size_t)g * 4 + 1] = c.upart_ptr[l];
     c.grp_info[(size_t)g * 4 + 2] = c.upart_ptr[l + 1] - c.upart_ptr[l];
+  }
+  {
+    // per-block partial sums of the block-resident PCG: plane l owns slots [ub_ptr[l], ub_ptr[l+1]), one per observing pose
+    // block in ascending block order (groups are numbered block by block, so a counting pass keeps that order)
+    std::vector<int> ub_ptr(M + 1, 0);
+    for (int g2 = 0; g2 < c.ngrp; g2++) ub_ptr[c.grp_plane[g2] + 1]++;
+    for (int l = 0; l < M; l++) ub_ptr[l + 1] += ub_ptr[l];
+    std::vector<int> fill(ub_ptr.begin(), ub_ptr.end() - 1);
+    c.grp_info2.assign((size_t)std::max(1, c.ngrp) * 4, 0);
+    for (int g2 = 0; g2 < c.ngrp; g2++) {
+      const int l = c.grp_plane[g2];
+      c.grp_info2[(size_t)g2 * 4] = l;
+      c.grp_info2[(size_t)g2 * 4 + 1] = ub_ptr[l];
+      c.grp_info2[(size_t)g2 * 4 + 2] = ub_ptr[l + 1] - ub_ptr[l];
+      c.grp_info2[(size_t)g2 * 4 + 3] = fill[l]++;
+    }
+    c.res_nt = c.res_ng = c.res_np = 0;
+    for (int k = 0; k < c.nblk; k++) {
+      c.res_nt = std::max(c.res_nt, c.tile_ptr[k + 1] - c.tile_ptr[k]);
+      c.res_ng = std::max(c.res_ng, c.blk_grp_ptr[k + 1] - c.blk_grp_ptr[k]);
+      c.res_np = std::max(c.res_np, c.blk_part_ptr[k + 1] - c.blk_part_ptr[k]);
+    }
   }
   // ---- (plane, node) pairs of the two hat levels ----
   auto build_pairs = [&](int SPx, std::vector<int>& ce_ptr, std::vector<int>& ce_node, std::vector<int>& ce_plane, std::vector<int>& ce_lo,

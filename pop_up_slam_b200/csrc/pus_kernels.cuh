@@ -48,6 +48,8 @@ struct LmParams {
   int tma_mode;      // 0: TMA-staged W/Wt tiles when a warp owns several tiles (large graphs), 1: always, 2: never
   int blocks_always; // 1: the dense 16-pose blocks (level 1) are rebuilt for every linear solve, only the coarse level(s) lazily
   int jac_numeric;   // 1: reference-Jacobian mode (central differences, numericalDiff.cpp:41-87) instead of the closed forms
+  int resident;      // 1: the PCG loop runs block-resident (pcg_resident: operator, preconditioner blocks and vectors of the owned
+                     //    pose blocks stay in shared memory / registers; set by the host when the layout fits the team)
 };
 
 struct LmResult {
@@ -83,6 +85,9 @@ struct DevGraph {
   const double *lp_meas, *lp_sinf;
   // dense-block groups, coarse pairs
   const int *blk_grp_ptr, *grp_plane, *grp_mem_ptr, *grp_mem, *blk_simple, *grp_info;
+  const int* grp_info2;         // block-resident PCG: {plane, first per-block partial, number of partials, own slot} per group
+  int res_nt, res_ng, res_np;   // largest tile / group / (tile, pose)-run count of any pose block
+  double* upartb;               // [ngrp][3] per-(block, plane) partial sums of W^T p
   const int *ce_ptr, *ce_node, *ce_plane, *ce_lo, *ce_hi, *n2ce_ptr, *n2ce;
   const int *hv_plane, *lp_ptr, *lp_cea, *lp_ceb, *fp_ptr, *fp_f;
   int n_hv;
@@ -108,6 +113,13 @@ struct DevGraph {
   LmTrace* trace;
 };
 
+// The graph descriptor of the solve in progress and the dynamic shared memory, named at namespace scope so that every
+// access compiles to LDS / STS with an immediate address (through a reference or a pointer kept in a struct they became
+// generic loads behind a local-memory load of the pointer -- on the critical path of every PCG phase).
+__shared__ DevGraph g_sG;
+extern __shared__ __align__(128) unsigned char g_smem[];
+#define G g_sG
+
 // ---------------------------------------------------------------------------------------------
 struct Ctx {
   int rank, tsize;       // CTA rank within its team, CTAs per team
@@ -127,6 +139,8 @@ struct Ctx {
   unsigned* gbar;
   unsigned gbar_target;  // thread 0 only
   unsigned char* smem;   // dynamic shared memory
+  unsigned long long* rflag;   // flag-stamped reduction slots of this team ([2 sets][tsize][2 words], zeroed by the host per launch)
+  unsigned red_seq;      // sequence number of the last flag-stamped reduction (same on every thread of the team)
 };
 
 __device__ __forceinline__ double ldc(const double* p) { return __ldcg(p); }
@@ -180,6 +194,29 @@ __device__ __forceinline__ void team_barrier(Ctx& c) {
       atomicAdd(c.bar, 1u);
       while ((int)(ld_acquire_u32(c.bar) - c.bar_target) < 0) { }
       __threadfence();
+    }
+    __syncthreads();
+  }
+}
+
+
+// Team barrier for the PCG loops, without the L1 invalidation that a gpu-scope fence or an acquire load implies (CCTL.IVALL
+// throws away every cached local-memory line of the SM -- the spilled loop state -- three times per PCG iteration).  Release
+// side: one release-reduction (orders the CTA's prior writes, through the CTA barrier, before the arrival).  Wait side:
+// relaxed polling; every value another CTA wrote is read with ld.global.cg (L2) inside those loops, so nothing stale in L1 can
+// be observed.  The full team_barrier() (fence + invalidate) brackets the loops.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void team_barrier_light(Ctx& c) {
+  __syncthreads();
+  if (c.tsize > 1) {
+    if (threadIdx.x == 0) {
+      c.bar_target += (unsigned)c.tsize;
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.bar), "r"(1u) : "memory");
+      while ((int)(ld_relaxed_u32(c.bar) - c.bar_target) < 0) { }
     }
     __syncthreads();
   }
@@ -301,7 +338,9 @@ constexpr int kPackedBlock = kBlockDim * (kBlockDim + 1) / 2;
 constexpr int kSmCache = 72 * 1024;                   // after the PCG work area (rc may use up to 72 KB - kSmRc)
 constexpr int kCacheBlocks = 4;
 constexpr int kSmCacheEnd = kSmCache + kCacheBlocks * kPackedBlock * 8;
-constexpr int kSmemBytes = (kSmBuildEnd > kSmCacheEnd ? kSmBuildEnd : kSmCacheEnd);  // (kSmTmaEnd <= kSmCacheEnd)  // >= kSmRc + 6*nc*8 is checked on the host
+constexpr int kSmemBytes = 225 * 1024;   // (almost) everything an SM offers next to the static DevGraph copy (>= kSmBuildEnd, kSmCacheEnd, kSmTmaEnd; kSmRc + 6*nc*8 and the
+                                         // block-resident layout are checked on the host)
+static_assert(kSmBuildEnd <= kSmemBytes && kSmCacheEnd <= kSmemBytes, "dynamic shared memory");
 static_assert(kSmPoseEnd <= kSmCache, "pose-phase buffers overlap the block cache");
 // TMA staging (large graphs; replaces the block cache): per warp two 4608-byte W / Wt tiles, filled by
 // cp.async.bulk and signalled through one mbarrier per stage
@@ -314,12 +353,43 @@ static_assert(kSmBar + kWarps * 2 * 8 <= kSmGjBar && kSmGjBar + 32 <= kSmWork, "
 static_assert(kSmTmaEnd <= 227 * 1024, "TMA staging buffers");
 static_assert(kSmemBytes <= 227 * 1024, "dynamic shared memory");
 
+
+// ---- block-resident PCG (pcg_resident): shared-memory layout of one CTA.  Every owned pose block ("slot") keeps, for the
+// whole linear solve, its W tiles, its packed preconditioner block, the packed static edge / group records and the
+// per-iteration scratch; the strides are the graph-wide maxima so that every CTA computes the same offsets.
+__host__ __device__ inline int r16(int x) { return (x + 15) & ~15; }
+constexpr int kResHeavy = 8;   // distinct heavy planes (seen from > 8 pose blocks) a CTA sums once for all its blocks
+struct ResLay {
+  int hdr, sP, sR, src, slot0, stride;       // header (tile / group counts per slot), direction, residual / q, coarse residual
+  int o_ei, o_gi, o_gm, o_mem, o_W, o_B;     // per slot: scratch at 0 (edge products | group vectors + run sums), then these
+  int total;
+};
+__host__ __device__ inline ResLay res_layout(int nt, int ng, int np, int ldm, int nown) {
+  ResLay L;
+  L.hdr = kSmWork;
+  L.sP = L.hdr + 64 + kResHeavy * 16 + kResHeavy * 16 * 3 * 8;   // + list of CTA-wide heavy planes and their per-warp partial sums
+  L.sR = L.sP + nown * kBlockDim * 8;
+  L.src = L.sR + nown * kBlockDim * 8;
+  L.slot0 = L.src + r16(ldm * 8);
+  const int ua = nt * 32 * 24, ub = r16(ng * 24) + np * 48;
+  const int uc = kBlockDim * 8;   // phase C: z of the block
+  L.o_ei = r16(ua > ub ? (ua > uc ? ua : uc) : (ub > uc ? ub : uc));
+  L.o_gi = L.o_ei + nt * 128;
+  L.o_gm = L.o_gi + ng * 16;
+  L.o_mem = L.o_gm + r16(ng * 8);
+  L.o_W = L.o_mem + r16(nt * 64);
+  L.o_B = L.o_W + nt * 18 * 32 * 8;
+  L.stride = L.o_B + kBlockDim * (kBlockDim + 1) / 2 * 8;
+  L.total = L.slot0 + nown * L.stride;
+  return L;
+}
+
 // deterministic team-wide sum of K (<= 4) values; result broadcast to every thread.
 // warp partials -> CTA partial (warp 0) -> global slot -> team barrier -> every CTA's warp 0 sums the
 // per-CTA partials with strided lanes + a shuffle tree (fixed order, so all CTAs get identical bits).
 template <int K>
 __device__ __forceinline__ void team_reduce(Ctx& c, double* red, double* v) {
-  double* s = reinterpret_cast<double*>(c.smem + kSmRed);
+  double* s = reinterpret_cast<double*>(g_smem + kSmRed);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
   for (int k = 0; k < K; k++) v[k] = warp_sum(v[k]);
@@ -354,6 +424,59 @@ __device__ __forceinline__ void team_reduce(Ctx& c, double* red, double* v) {
   __syncthreads();
 #pragma unroll
   for (int k = 0; k < K; k++) v[k] = s[kWarps * 4 + k];
+}
+
+
+// Team-wide sum of one value without an atomic counter: every CTA stamps its partial with the reduction's sequence number
+// (two 8-byte words {value half, seq}, each store single-copy atomic) and warp 0 of every CTA polls all the slots until they
+// carry that number, then adds them in a fixed order (identical bits on every CTA).  One store + one polled load instead of
+// store, atomic, polled counter, load.  Double-buffered: a CTA can start reduction n+2 only after every CTA has read n.
+// Memory ordering as in team_barrier_light: CTA barrier, release store of the second word, relaxed polling, L2 reads.
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double team_reduce_flag(Ctx& c, double v) {
+  double* s = reinterpret_cast<double*>(g_smem + kSmRed);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  v = warp_sum(v);
+  __syncthreads();  // protect s from a previous use; all global writes of the phase are done
+  if (lane == 0) s[warp * 4] = v;
+  __syncthreads();
+  c.red_seq++;
+  if (warp == 0) {
+    double acc = (lane < kWarps) ? s[lane * 4] : 0.0;
+    acc = warp_sum(acc);
+    if (c.tsize > 1) {
+      const unsigned seq = c.red_seq;
+      unsigned long long* slots = c.rflag + (size_t)(seq & 1u) * c.tsize * 2;
+      if (lane == 0) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(acc);
+        st_relaxed_u64(slots + (size_t)c.rank * 2, (b & 0xffffffffull) | ((unsigned long long)seq << 32));
+        st_release_u64(slots + (size_t)c.rank * 2 + 1, (b >> 32) | ((unsigned long long)seq << 32));   // (orders every prior write)
+      }
+      double tot = 0;
+      for (int r = lane; r < c.tsize; r += 32) {
+        unsigned long long w0, w1;
+        do {
+          w0 = ld_relaxed_u64(slots + (size_t)r * 2);
+          w1 = ld_relaxed_u64(slots + (size_t)r * 2 + 1);
+        } while ((unsigned)(w0 >> 32) != seq || (unsigned)(w1 >> 32) != seq);
+        tot += __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+      }
+      acc = warp_sum(tot);
+    }
+    if (lane == 0) s[kWarps * 4] = acc;
+  }
+  __syncthreads();
+  return s[kWarps * 4];
 }
 
 // segmented (by sorted key) suffix sums inside a warp: afterwards the first lane of every run of equal
@@ -436,7 +559,7 @@ struct Timer {
   bool on;
   unsigned long long t0;
   unsigned long long* acc;
-  __device__ Timer(bool o, unsigned char* smem) : on(o), t0(0), acc(reinterpret_cast<unsigned long long*>(smem + kSmTimer)) {
+  __device__ Timer(bool o) : on(o), t0(0), acc(reinterpret_cast<unsigned long long*>(g_smem + kSmTimer)) {
     if (on) { for (int i = 0; i < 24; i++) acc[i] = 0; t0 = gtime(); }
   }
   __device__ void sync() { if (on) t0 = gtime(); }
@@ -530,11 +653,13 @@ __device__ __noinline__ void pose_plane2_linearize(const double* pose, const dou
 }
 
 struct Phase {
-  const DevGraph& G;
   Ctx& c;
   Timer* ft = nullptr;  // optional fine-grained phase timer (lead thread)
-  __device__ Phase(const DevGraph& g, Ctx& cc) : G(g), c(cc) {}
+  __device__ Phase(Ctx& cc) : c(cc) {}
   __device__ __forceinline__ void lap(int slot) { if (ft) ft->lap(slot); }
+  // slots 6 / 22 / 23 are shared: sub-stages of the resident PCG loop (fine_timers == 1) or of linearize (fine_timers == 2)
+  __device__ __forceinline__ void lap1(int slot) { if (ft && G.prm.fine_timers == 1) ft->lap(slot); }
+  __device__ __forceinline__ void lap2(int slot) { if (ft && G.prm.fine_timers == 2) ft->lap(slot); }
 
   __device__ __forceinline__ int tid_team() const { return c.rank * kThreads + threadIdx.x; }
   __device__ __forceinline__ int nthr_team() const { return c.tsize * kThreads; }
@@ -761,12 +886,12 @@ struct Phase {
   // -------- Schur setup, part 2: dense diagonal blocks of S, inverted in shared memory --------
   __device__ void build_blocks(double lambda) {
     constexpr int LD = kLdS;
-    double* S0 = reinterpret_cast<double*>(c.smem + kSmS0);
-    double* S1 = reinterpret_cast<double*>(c.smem + kSmS1);
-    double* Wg = reinterpret_cast<double*>(c.smem + kSmWg);
-    double* Yg = reinterpret_cast<double*>(c.smem + kSmYg);
-    double* TQ = reinterpret_cast<double*>(c.smem + kSmP);
-    double* His = reinterpret_cast<double*>(c.smem + kSmHi);
+    double* S0 = reinterpret_cast<double*>(g_smem + kSmS0);
+    double* S1 = reinterpret_cast<double*>(g_smem + kSmS1);
+    double* Wg = reinterpret_cast<double*>(g_smem + kSmWg);
+    double* Yg = reinterpret_cast<double*>(g_smem + kSmYg);
+    double* TQ = reinterpret_cast<double*>(g_smem + kSmP);
+    double* His = reinterpret_cast<double*>(g_smem + kSmHi);
     const int tid = threadIdx.x;
     for (int k = c.rank; k < G.nblk; k += c.tsize) {
       const int p0 = k * kBlockPoses;
@@ -1011,12 +1136,12 @@ struct Phase {
   // the group as a dense rank-3 update from the staged Yc2 / Wc2 rows.  Fixed summation order, no atomics.
   __device__ void build_groups(double lambda) {
     constexpr int LD = kLdS;
-    double* S0 = reinterpret_cast<double*>(c.smem + kSmS0);
-    double* S1 = reinterpret_cast<double*>(c.smem + kSmS1);
-    double* Yst = reinterpret_cast<double*>(c.smem + kSmWg);   // [<=16][18]
-    double* Wst = reinterpret_cast<double*>(c.smem + kSmYg);   // [<=16][18]
-    double* TQ = reinterpret_cast<double*>(c.smem + kSmP);
-    int* nloc = reinterpret_cast<int*>(c.smem + kSmHi);        // node of the staged rows, relative to the group
+    double* S0 = reinterpret_cast<double*>(g_smem + kSmS0);
+    double* S1 = reinterpret_cast<double*>(g_smem + kSmS1);
+    double* Yst = reinterpret_cast<double*>(g_smem + kSmWg);   // [<=16][18]
+    double* Wst = reinterpret_cast<double*>(g_smem + kSmYg);   // [<=16][18]
+    double* TQ = reinterpret_cast<double*>(g_smem + kSmP);
+    int* nloc = reinterpret_cast<int*>(g_smem + kSmHi);        // node of the staged rows, relative to the group
     const int tid = threadIdx.x;
     for (int g = c.rank; g < G.ng2; g += c.tsize) {
       const int a0 = g * kGroupNodes;
@@ -1091,7 +1216,7 @@ struct Phase {
   __device__ void coarse_assemble(double lambda) {
     const int ldm = G.ldmc, nc = G.nc, n6 = 6 * nc;
     double* A = G.Ac[0];
-    double* Yh = reinterpret_cast<double*>(c.smem + kSmWork);   // [nc][18]
+    double* Yh = reinterpret_cast<double*>(g_smem + kSmWork);   // [nc][18]
     double* Wh = Yh + (size_t)nc * 18;                          // [nc][18]
     const int npass = max(1, G.n_hv);
     const long long total = (long long)ldm * ldm;
@@ -1164,7 +1289,7 @@ struct Phase {
     constexpr int LDT = kGjLdT, LDR = kGjLdR;  // padded strides: the DMMA fragment loads are bank-conflict free
     const int ldm = G.ldmc, nsteps = ldm / PW;
     constexpr int LDP = kGjLdP, LDQ = kGjLdQ;
-    double* Pa = reinterpret_cast<double*>(c.smem + kSmWork);  // [PW][LDP] pivot block (ping)
+    double* Pa = reinterpret_cast<double*>(g_smem + kSmWork);  // [PW][LDP] pivot block (ping)
     double* Pb = Pa + PW * LDP;                                // [PW][LDP] (pong); ends up holding the inverse
     double* TQ = Pb + PW * LDP;                                // [PW][LDQ] coefficient columns of the inner block step
     const int R = gj_band_rows(ldm, c.tsize);                  // rows per CTA (whole 8-row MMA tiles)
@@ -1184,7 +1309,7 @@ struct Phase {
       for (int i = tid; i < PW * PW; i += kThreads) Pa[(i / PW) * LDP + i % PW] = ldc(src + ac_index(ldm, k0 + i / PW, k0 + i % PW));
       for (int i = tid; i < band * PW; i += kThreads) Ab[i] = ldc(src + ac_index(ldm, r0 + i / PW, k0 + i % PW));
       __syncthreads();
-      lap(6);
+      lap1(6);
       // inversion of the 48x48 pivot block (SPD: no pivoting), see gj_invert_smem()
       const double* Pm = gj_invert_smem<PW / 8, LDP>(Pa, Pb, TQ);
       lap(7);
@@ -1212,7 +1337,7 @@ struct Phase {
       // in flight while this one is multiplied); warp w owns the chunk's w-th 8-column tile and up to two 8-row
       // tiles of the band per pass: mma.m8n8k4 with A = Tn fragment, B = panel fragment, C = base (prefetched).
       const int nchunk = (ldm + CW - 1) / CW;
-      unsigned long long* gbar = reinterpret_cast<unsigned long long*>(c.smem + kSmGjBar);
+      unsigned long long* gbar = reinterpret_cast<unsigned long long*>(g_smem + kSmGjBar);
       auto issue = [&](int ci) {   // one bulk copy per chunk: tile (k, ci) of the source, padded stride included
         if (tid == 0) {
           double* buf = Rc + (ci & 1) * PW * LDR;
@@ -1300,9 +1425,7 @@ struct Phase {
         __syncthreads();   // the buffer is free for chunk ci + 2
       }
       fence_proxy_async();  // the other CTAs' bulk copies read these rows in the next step
-      lap(22);
       team_barrier(c);
-      lap(23);
       cur ^= 1;
     }
     return cur;
@@ -1318,8 +1441,8 @@ struct Phase {
       // (4608 contiguous bytes) is in flight as one bulk async copy into the other staging buffer, the per-edge
       // gathers of the next tile are issued before this tile is multiplied, and the edge indices are read two tiles
       // ahead -- no dependent-load latency is exposed in steady state.
-      double* buf = reinterpret_cast<double*>(c.smem + kSmTma) + warp * 2 * kWStride;
-      unsigned long long* bar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + warp * 2;
+      double* buf = reinterpret_cast<double*>(g_smem + kSmTma) + warp * 2 * kWStride;
+      unsigned long long* bar = reinterpret_cast<unsigned long long*>(g_smem + kSmBar) + warp * 2;
       int tile = warp_team(), st = 0;
       __syncwarp();
       if (lane == 0 && tile < G.ntile_pl) {
@@ -1433,7 +1556,7 @@ struct Phase {
     for (int hh = c.rank; hh < G.n_huge; hh += c.tsize) {
       const int l = G.huge[hh];
       const int t0 = G.upart_ptr[l], n = G.upart_ptr[l + 1] - t0;
-      double* s = reinterpret_cast<double*>(c.smem + kSmRed);
+      double* s = reinterpret_cast<double*>(g_smem + kSmRed);
       double uu[3] = {0, 0, 0};
       for (int tb = t0 + (int)threadIdx.x; tb < t0 + n; tb += 4 * kThreads) {
         double pr[4][3];
@@ -1518,13 +1641,13 @@ struct Phase {
   //   3. apply: q = (Hpp + lambda diag) p + (pose-pose blocks) p_other - y ; qc = P^T q ; returns partial p.q
   //      rhs  : b = -gp + y ; x = 0, r = b, p = z = q = 0 ; rcpart[0] = P^T b
   __device__ double pose_phase(bool rhs, const double* pvec, double lambda, double* qout, double* qc) {
-    double* sA = reinterpret_cast<double*>(c.smem + kSmA);
-    double* vg = reinterpret_cast<double*>(c.smem + kSmVg);
-    double* yp = reinterpret_cast<double*>(c.smem + kSmYp);
+    double* sA = reinterpret_cast<double*>(g_smem + kSmA);
+    double* vg = reinterpret_cast<double*>(g_smem + kSmVg);
+    double* yp = reinterpret_cast<double*>(g_smem + kSmYp);
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
     const int lane = tid & 31, wis = u >> 5;  // warp within the slot (3 warps per slot)
-    double* tbuf = reinterpret_cast<double*>(c.smem + kSmTma) + (tid >> 5) * 2 * kWStride;  // TMA staging (large graphs)
-    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(c.smem + kSmBar) + (tid >> 5) * 2;
+    double* tbuf = reinterpret_cast<double*>(g_smem + kSmTma) + (tid >> 5) * 2 * kWStride;  // TMA staging (large graphs)
+    unsigned long long* tbar = reinterpret_cast<unsigned long long*>(g_smem + kSmBar) + (tid >> 5) * 2;
     double dot = 0;
     const int nrounds = rounds();
     // plane-group record of this thread for the coming round (static data, read one round ahead)
@@ -1735,7 +1858,7 @@ struct Phase {
 
   // -------- PCG: copy the owned dense blocks (upper triangles) into shared memory for the whole solve ----
   __device__ void cache_blocks() {
-    double* cache = reinterpret_cast<double*>(c.smem + kSmCache);
+    double* cache = reinterpret_cast<double*>(g_smem + kSmCache);
     __syncthreads();
     for (int ci = 0; ci < kCacheBlocks; ci++) {
       // cached block ci of this CTA = owned block of (slot = ci % kSlots, round = ci / kSlots)
@@ -1751,8 +1874,8 @@ struct Phase {
   // over the team, or applied by every CTA when the level is small); level-2 nodes: one warp per node = its 6 rows of the
   // group's 96 x 96 inverse.  Publishes zc2 (and zc when level 3 is distributed); returns the partial of r.z it owns.
   __device__ double coarse_three_level(double alpha, int acinv, const double* rc_old, bool first) {
-    double* src = reinterpret_cast<double*>(c.smem + kSmRc);   // level-3 residual [6 nc]
-    double* z3s = reinterpret_cast<double*>(c.smem + kSmZc);   // level-3 solution when it is applied locally (<= kL3Local rows)
+    double* src = reinterpret_cast<double*>(g_smem + kSmRc);   // level-3 residual [6 nc]
+    double* z3s = reinterpret_cast<double*>(g_smem + kSmZc);   // level-3 solution when it is applied locally (<= kL3Local rows)
     const int tid = threadIdx.x, lane = tid & 31;
     const int ldm = 6 * G.nc, m = G.SP / kL2Spacing;
     // level-2 residual of node a: per-block partials of the previous iteration, updated linearly (r_new = r - alpha q)
@@ -1874,8 +1997,8 @@ struct Phase {
   // rc_old / rc_new: ping-pong buffers of per-block coarse restrictions of r
   __device__ double precondition(double alpha, const double* pvec, int acinv, const double* rc_old, double* rc_new,
                                  bool first) {
-    double* sA = reinterpret_cast<double*>(c.smem + kSmA);   // r_new per slot
-    double* src = reinterpret_cast<double*>(c.smem + kSmRc); // coarse residual, 6*nc
+    double* sA = reinterpret_cast<double*>(g_smem + kSmA);   // r_new per slot
+    double* src = reinterpret_cast<double*>(g_smem + kSmRc); // coarse residual, 6*nc
     const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim;
     const int ldm = 6 * G.nc;
     const int bpn = G.SP / kBlockPoses;  // blocks per coarse interval
@@ -1993,7 +2116,7 @@ struct Phase {
       // Large graphs: (A) update x, r of every owned pose and keep the new residuals of all rounds in shared memory
       // (loads of three rounds in flight together), then (B) stream the owned dense blocks Binv[k] through the
       // two 72 KB staging buffers with one bulk async copy each (the next block in flight while this one is applied).
-      double* sR = reinterpret_cast<double*>(c.smem + sr_off);
+      double* sR = reinterpret_cast<double*>(g_smem + sr_off);
       __syncthreads();
       for (int rd0 = 0; rd0 < nrd; rd0 += 3) {
         double vr[3], vp[3], vq[3], vx[3];
@@ -2023,8 +2146,8 @@ struct Phase {
         }
       }
       __syncthreads();
-      unsigned long long* gbar = reinterpret_cast<unsigned long long*>(c.smem + kSmGjBar);
-      double* bbuf = reinterpret_cast<double*>(c.smem + kSmTma);
+      unsigned long long* gbar = reinterpret_cast<unsigned long long*>(g_smem + kSmGjBar);
+      double* bbuf = reinterpret_cast<double*>(g_smem + kSmTma);
       constexpr unsigned kBlockBytes = kPackedBlock * 8;   // packed upper triangle: 37 248 bytes, one bulk copy
       static_assert(kBlockBytes % 16 == 0 && 2 * kBlockBytes <= kSmTmaEnd - kSmTma, "two packed blocks must fit the staging area");
       const int nown = (G.nblk - c.rank + c.tsize - 1) / c.tsize;   // owned blocks: k = rank + tsize * ib
@@ -2093,7 +2216,7 @@ struct Phase {
         double zl = 0;
         const int ci = slot + kSlots * rd;
         if (ci < kCacheBlocks && (c.smem_cache_ok)) {
-          const double* cb = reinterpret_cast<const double*>(c.smem + kSmCache) + (size_t)ci * kPackedBlock;
+          const double* cb = reinterpret_cast<const double*>(g_smem + kSmCache) + (size_t)ci * kPackedBlock;
           const double* rv = sA + slot * kBlockDim;
           // rows j < u: element (j,u) ; rows j >= u: element (u,j)
           for (int j = 0; j < u; j++) zl += cb[j * kBlockDim - (j * (j - 1)) / 2 + (u - j)] * rv[j];
@@ -2112,6 +2235,462 @@ struct Phase {
     }
     lap(15);
     return dot;
+  }
+
+
+  // -------- block-resident PCG loop (graphs whose owned blocks fit one CTA's shared memory; single-GPU, two levels) --------
+  // Same recurrence, operator and preconditioner as the loop in schur_solve(), reorganised so that an iteration touches L2
+  // only for what CTAs really exchange:
+  //   A  p = z + P zc + beta p (registers / smem) ; W^T p of the OWN pose-major tiles from the smem copy of W ; fixed-order sums
+  //      per (block, plane) group -> upartb ; p published for pose-pose neighbours in other blocks            -> team barrier
+  //   B  v_g = Hll^-1 * (sum of the plane's per-block partials) ; y = W v from smem ; q = (Hpp + lambda D) p + pose-pose - y ;
+  //      P^T q -> qcpart ; p.q                                                                                 -> team reduction
+  //   C  coarse residual (linear update) ; A_c^-1 rows -> zc ; x, r updated in registers ; z = Binv r from smem ; r.z -> reduction
+  // r, x, z, p, q of a row live in the registers of its thread for the whole solve.  Entry state (from the common prologue):
+  // G.r, G.x, G.z (local part), G.zc, rcpart[rcb] ; exit: G.x.  Returns the iteration count.
+  __device__ int pcg_resident(double lambda, int acinv, int rcb, const double rz0, double rz, const double tol2, Timer& tmr) {
+    const int ldm = 6 * G.nc;
+    const int nown_max = (G.nblk + c.tsize - 1) / c.tsize;
+    const ResLay L = res_layout(G.res_nt, G.res_ng, G.res_np, ldm, nown_max);
+    const int tid = threadIdx.x, slot = tid / kBlockDim, u = tid % kBlockDim, lane = tid & 31, warp = tid >> 5, wis = u >> 5;
+    const int nown = (G.nblk - c.rank + c.tsize - 1) / c.tsize;   // owned blocks k = rank + tsize * slot
+    int* hdr = reinterpret_cast<int*>(g_smem + L.hdr);            // [0..7] tiles per slot, [8..15] groups per slot
+    double* sP = reinterpret_cast<double*>(g_smem + L.sP);
+    double* sR = reinterpret_cast<double*>(g_smem + L.sR);
+    double* src = reinterpret_cast<double*>(g_smem + L.src);
+    __syncthreads();
+    // ---- static per-solve caches ----
+    for (int s = 0; s < nown; s++) {
+      const int kb = c.rank + c.tsize * s;
+      unsigned char* sb = g_smem + L.slot0 + s * L.stride;
+      const int t0 = G.tile_ptr[kb], nt = G.tile_ptr[kb + 1] - t0, e0 = t0 * 32;
+      const int g0 = G.blk_grp_ptr[kb], ng = G.blk_grp_ptr[kb + 1] - g0, part0 = G.blk_part_ptr[kb];
+      if (tid == 0) { hdr[s] = nt; hdr[8 + s] = ng; }
+      int* ei = reinterpret_cast<int*>(sb + L.o_ei);
+      for (int e = tid; e < nt * 32; e += kThreads) {
+        const int pp = G.pp_pose[e0 + e];
+        ei[e] = pp < 0 ? 31 : ((pp - kb * kBlockPoses) | (G.grp_of_slot[e0 + e] << 5) | ((G.pm_part[e0 + e] - part0) << 14));
+      }
+      int4* gi = reinterpret_cast<int4*>(sb + L.o_gi);
+      int2* gm = reinterpret_cast<int2*>(sb + L.o_gm);
+      unsigned short* mem = reinterpret_cast<unsigned short*>(sb + L.o_mem);
+      const int mb = G.grp_mem_ptr[g0];
+      for (int g = tid; g < ng; g += kThreads) {
+        gi[g] = *reinterpret_cast<const int4*>(G.grp_info2 + (size_t)(g0 + g) * 4);
+        const int m0 = G.grp_mem_ptr[g0 + g], m1 = G.grp_mem_ptr[g0 + g + 1];
+        gm[g] = make_int2(m0 - mb, m1 - m0);
+      }
+      const int nm = G.grp_mem_ptr[g0 + ng] - mb;
+      for (int m = tid; m < nm; m += kThreads) mem[m] = (unsigned short)(G.grp_mem[mb + m] - e0);
+      double* Wc = reinterpret_cast<double*>(sb + L.o_W);
+      const double* Wg = G.W + (size_t)t0 * kWStride;
+      for (int i = tid; i < nt * kWStride; i += kThreads) Wc[i] = ldc(Wg + i);
+      double* Bc = reinterpret_cast<double*>(sb + L.o_B);
+      const double* Bg = G.Binv + (size_t)kb * kPackedBlock;
+      for (int i = tid; i < kPackedBlock; i += kThreads) Bc[i] = ldc(Bg + i);
+    }
+    // ---- per-thread state: row `row` of pose p in owned block k ----
+    const bool live = slot < nown;
+    const int k = c.rank + c.tsize * (live ? slot : 0);
+    const int p = k * kBlockPoses + u / 6, row = u % 6;
+    const bool on = live && p < G.N;
+    const int np = live ? min(kBlockPoses, G.N - k * kBlockPoses) : 0;
+    const size_t o = (size_t)p * 6 + row;
+    unsigned char* sb = g_smem + L.slot0 + (live ? slot : 0) * L.stride;
+    double* sE = reinterpret_cast<double*>(sb);                    // phase A: per-edge W_e^T p  [tiles * 32][3]
+    double* vg = reinterpret_cast<double*>(sb);                    // phase B: plane-group vectors [ng][3] ...
+    double* yp = reinterpret_cast<double*>(sb + r16(G.res_ng * 24));   // ... and (tile, pose)-run sums [np][6]
+    const int4* gi = reinterpret_cast<const int4*>(sb + L.o_gi);
+    const int2* gm = reinterpret_cast<const int2*>(sb + L.o_gm);
+    const unsigned short* mem = reinterpret_cast<const unsigned short*>(sb + L.o_mem);
+    const double* Bc = reinterpret_cast<const double*>(sb + L.o_B);
+    double r_u = 0, x_u = 0, z_u = 0, p_u = 0, q_u = 0;
+    int yp0 = 0, ypn = 0;
+    int4 nb = make_int4(-1, -1, -1, -1);
+    int2 nr = make_int2(0, 0);
+    if (on) {
+      r_u = ldc(G.r + o); x_u = ldc(G.x + o); z_u = ldc(G.z + o);
+      yp0 = G.ypart_ptr[p] - G.blk_part_ptr[k];
+      ypn = G.ypart_ptr[p + 1] - G.ypart_ptr[p];
+      nb = *reinterpret_cast<const int4*>(G.pnbr + (size_t)p * 8);
+      nr = *reinterpret_cast<const int2*>(G.pnbr + (size_t)p * 8 + 4);
+    }
+    // row `row` of pose p of the pose part of the operator, static for this solve: (Hpp + lambda D) row and the rows of the
+    // pose-pose blocks towards the first two neighbours (the odometry chain).  Kept per thread for the whole loop (registers or,
+    // spilled, lane-interleaved local memory = coalesced) instead of 18 scattered 8-byte loads per iteration.
+    double trow[18];
+#pragma unroll
+    for (int t = 0; t < 18; t++) trow[t] = 0.0;
+    const int nf = (nb.x >= 0) + (nb.z >= 0);
+    const int oth0 = max(nb.y, 0), oth1 = max(nb.w, 0);
+    if (on) {
+      const double* H = G.Hpp + (size_t)p * 36 + row * 6;
+#pragma unroll
+      for (int cc = 0; cc < 6; cc++) trow[cc] = ldc(H + cc) * (cc == row ? (1 + lambda) : 1.0);
+      const double* Ab[2] = {G.PF + (size_t)(max(nb.x, 0) >> 1) * 120 + 72, G.PF + (size_t)(max(nb.z, 0) >> 1) * 120 + 72};
+      const int sd[2] = {nb.x & 1, nb.z & 1};
+#pragma unroll
+      for (int n2 = 0; n2 < 2; n2++)
+#pragma unroll
+        for (int cc = 0; cc < 6; cc++)
+          trow[6 + n2 * 6 + cc] = (n2 < nf) ? (sd[n2] ? ldc(Ab[n2] + cc * 6 + row) : ldc(Ab[n2] + row * 6 + cc)) : 0.0;
+    }
+    __syncthreads();
+    // planes seen from more than 8 pose blocks (the ground plane from all): summed once per CTA by all its warps instead of
+    // once per owned block -- a list of the distinct ones among this CTA's groups; a listed group carries -(index + 1) as its
+    // partial count.  (More than kResHeavy distinct ones: the rest keep the per-block warp loop.)
+    int* hvl = reinterpret_cast<int*>(g_smem + L.hdr + 64);   // [kResHeavy][4] = {plane, first partial, count, -}
+    if (tid == 0) {
+      int nh = 0;
+      for (int s = 0; s < nown; s++) {
+        int4* gs = reinterpret_cast<int4*>(g_smem + L.slot0 + s * L.stride + L.o_gi);
+        for (int g = 0; g < hdr[8 + s]; g++) {
+          const int4 q = gs[g];
+          if (q.z <= 8) continue;
+          int h = 0;
+          while (h < nh && hvl[h * 4] != q.x) h++;
+          if (h == nh) {
+            if (nh == kResHeavy) continue;
+            hvl[h * 4] = q.x; hvl[h * 4 + 1] = q.y; hvl[h * 4 + 2] = q.z;
+            nh++;
+          }
+          gs[g].z = -(h + 1);
+        }
+      }
+      hdr[7] = nh;
+    }
+    __syncthreads();
+    const int ng = live ? hdr[8 + slot] : 0;
+    const int nh = hdr[7];
+    int wpe = kWarps;   // warps per listed plane (power of two)
+    while (wpe > 1 && wpe * nh > kWarps) wpe >>= 1;
+    double* hvp = reinterpret_cast<double*>(g_smem + L.hdr + 64 + kResHeavy * 16);   // [kResHeavy][kWarps][3] partial sums
+    const double* Ai = G.Ac[acinv];
+    double* pvec = G.pv[0];
+    int it = 0;
+    double beta = 0.0;
+    while (it < G.prm.pcg_max_iter) {
+      tmr.sync();
+      // ================= A =================
+      if (on) {
+        const int d = p - k * kBlockPoses;
+        const double h1 = (double)d * (1.0 / kBlockPoses);
+        const double cz = (1.0 - h1) * ldc(G.zc + (size_t)k * 6 + row) + h1 * ldc(G.zc + (size_t)min(k + 1, G.nc - 1) * 6 + row);
+        p_u = (z_u + cz) + beta * p_u;
+        pvec[o] = p_u;
+      }
+      if (live) sP[slot * kBlockDim + u] = on ? p_u : 0.0;
+      __syncthreads();
+      {
+        int cnt = 0;
+        for (int s = 0; s < nown; s++) {
+          const int nts = hdr[s];
+          for (int t = 0; t < nts; t++, cnt++) {
+            if ((cnt & (kWarps - 1)) != warp) continue;
+            unsigned char* sbs = g_smem + L.slot0 + s * L.stride;
+            const int info = reinterpret_cast<const int*>(sbs + L.o_ei)[t * 32 + lane];
+            const int pe = info & 31;
+            double uu[3] = {0, 0, 0};
+            if (pe != 31) {
+              const double* xs = sP + s * kBlockDim + pe * 6;
+              const double* w = reinterpret_cast<const double*>(sbs + L.o_W) + t * kWStride + lane;
+#pragma unroll
+              for (int a = 0; a < 6; a++) {
+                const double xa = xs[a];
+#pragma unroll
+                for (int b = 0; b < 3; b++) uu[b] += w[(a * 3 + b) * 32] * xa;
+              }
+            }
+            double* se = reinterpret_cast<double*>(sbs) + (size_t)(t * 32 + lane) * 3;
+            se[0] = uu[0]; se[1] = uu[1]; se[2] = uu[2];
+          }
+        }
+      }
+      __syncthreads();
+      if (live) {
+        for (int g = u; g < ng; g += kBlockDim) {
+          const int2 m = gm[g];
+          double s0 = 0, s1 = 0, s2 = 0;
+          for (int i = 0; i < m.y; i++) {
+            const double* se = sE + (size_t)mem[m.x + i] * 3;
+            s0 += se[0]; s1 += se[1]; s2 += se[2];
+          }
+          double* uo = G.upartb + (size_t)gi[g].w * 3;
+          uo[0] = s0; uo[1] = s1; uo[2] = s2;
+        }
+      }
+      team_barrier_light(c);
+      tmr.lap(16);
+      // ================= B =================
+      if (live) {
+        for (int g = u; g < ng; g += kBlockDim) {
+          const int4 gq = gi[g];
+          const int l = gq.x, t0 = gq.y, n = gq.z;
+          if (n >= 0 && n <= 8) {
+            double pr[8][3], Hi[9];
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) pr[t][b] = (t < n) ? ldc(G.upartb + (size_t)(t0 + t) * 3 + b) : 0.0;
+#pragma unroll
+            for (int t = 0; t < 9; t++) Hi[t] = ldc(G.Hinv + (size_t)l * 9 + t);
+            double uu[3] = {0, 0, 0};
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
+#pragma unroll
+            for (int b = 0; b < 3; b++) vg[g * 3 + b] = Hi[b * 3] * uu[0] + Hi[b * 3 + 1] * uu[1] + Hi[b * 3 + 2] * uu[2];
+          }
+        }
+        for (int g = wis; g < ng; g += 3) {   // unlisted planes seen from more than 8 pose blocks: a warp of the block sums the partials
+          const int4 gq = gi[g];
+          const int l = gq.x, t0 = gq.y, n = gq.z;
+          if (n <= 8) continue;
+          double uu[3] = {0, 0, 0};
+          for (int tb = t0 + lane; tb < t0 + n; tb += 256) {
+            double pr[8][3];
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) pr[t][b] = (tb + 32 * t < t0 + n) ? ldc(G.upartb + (size_t)(tb + 32 * t) * 3 + b) : 0.0;
+#pragma unroll
+            for (int t = 0; t < 8; t++)
+#pragma unroll
+              for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
+          }
+          for (int b = 0; b < 3; b++) uu[b] = warp_sum(uu[b]);
+          if (lane < 3)
+            vg[g * 3 + lane] = ldc(G.Hinv + (size_t)l * 9 + lane * 3) * uu[0] + ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 1) * uu[1] +
+                               ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 2) * uu[2];
+        }
+      }
+      lap1(22);
+      // listed heavy planes: `wpe` warps each, every warp one contiguous chunk of the plane's per-block partials
+      double hHi[9];
+      int hidx = -1, hg = -1;
+      if (live)
+        for (int g = u; g < ng; g += kBlockDim)
+          if (gi[g].z < 0) {   // (at most one listed group per thread: ng <= 96 here, else the tail loop below)
+            hg = g; hidx = -gi[g].z - 1;
+#pragma unroll
+            for (int t = 0; t < 9; t++) hHi[t] = ldc(G.Hinv + (size_t)gi[g].x * 9 + t);
+            break;
+          }
+      if (warp < nh * wpe) {
+        const int h = warp / wpe, j = warp - h * wpe;
+        const int t0 = hvl[h * 4 + 1], n = hvl[h * 4 + 2];
+        const int per = (n + wpe - 1) / wpe, a0 = t0 + j * per, a1 = min(t0 + n, a0 + per);
+        double uu[3] = {0, 0, 0};
+        for (int tb = a0 + lane; tb < a1; tb += 256) {
+          double pr[8][3];
+#pragma unroll
+          for (int t = 0; t < 8; t++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) pr[t][b] = (tb + 32 * t < a1) ? ldc(G.upartb + (size_t)(tb + 32 * t) * 3 + b) : 0.0;
+#pragma unroll
+          for (int t = 0; t < 8; t++)
+#pragma unroll
+            for (int b = 0; b < 3; b++) uu[b] += pr[t][b];
+        }
+        for (int b = 0; b < 3; b++) uu[b] = warp_sum(uu[b]);
+        if (lane < 3) hvp[(h * kWarps + j) * 3 + lane] = (lane == 0) ? uu[0] : (lane == 1 ? uu[1] : uu[2]);
+      }
+      lap1(23);
+      if (nh) {
+        __syncthreads();
+        if (hidx >= 0) {
+          double uu[3] = {0, 0, 0};
+          for (int j = 0; j < wpe; j++)
+            for (int b = 0; b < 3; b++) uu[b] += hvp[(hidx * kWarps + j) * 3 + b];
+          for (int b = 0; b < 3; b++) vg[hg * 3 + b] = hHi[b * 3] * uu[0] + hHi[b * 3 + 1] * uu[1] + hHi[b * 3 + 2] * uu[2];
+          for (int g = hg + kBlockDim; g < ng; g += kBlockDim)   // (blocks with more than 96 groups: further listed groups of this thread)
+            if (gi[g].z < 0) {
+              const int hi2 = -gi[g].z - 1, l2 = gi[g].x;
+              double u2[3] = {0, 0, 0};
+              for (int j = 0; j < wpe; j++)
+                for (int b = 0; b < 3; b++) u2[b] += hvp[(hi2 * kWarps + j) * 3 + b];
+              for (int b = 0; b < 3; b++)
+                vg[g * 3 + b] = ldc(G.Hinv + (size_t)l2 * 9 + b * 3) * u2[0] + ldc(G.Hinv + (size_t)l2 * 9 + b * 3 + 1) * u2[1] +
+                                ldc(G.Hinv + (size_t)l2 * 9 + b * 3 + 2) * u2[2];
+            }
+        }
+      }
+      __syncthreads();
+      lap(21);
+      {
+        int cnt = 0;
+        for (int s = 0; s < nown; s++) {
+          const int nts = hdr[s];
+          for (int t = 0; t < nts; t++, cnt++) {
+            if ((cnt & (kWarps - 1)) != warp) continue;
+            unsigned char* sbs = g_smem + L.slot0 + s * L.stride;
+            const int info = reinterpret_cast<const int*>(sbs + L.o_ei)[t * 32 + lane];
+            const int pe = info & 31, key = (pe == 31) ? -1 : pe;
+            double y[6] = {0, 0, 0, 0, 0, 0};
+            if (key >= 0) {
+              const double* vv = reinterpret_cast<const double*>(sbs) + ((info >> 5) & 511) * 3;
+              const double v0 = vv[0], v1 = vv[1], v2 = vv[2];
+              const double* w = reinterpret_cast<const double*>(sbs + L.o_W) + t * kWStride + lane;
+#pragma unroll
+              for (int a = 0; a < 6; a++) y[a] = w[(a * 3) * 32] * v0 + w[(a * 3 + 1) * 32] * v1 + w[(a * 3 + 2) * 32] * v2;
+            }
+            seg_suffix_sum<6>(key, y);
+            const int pk = __shfl_up_sync(0xffffffffu, key, 1);
+            if (key >= 0 && (lane == 0 || pk != key)) {
+              double* yo = reinterpret_cast<double*>(sbs + r16(G.res_ng * 24)) + (size_t)(info >> 14) * 6;
+#pragma unroll
+              for (int a = 0; a < 6; a++) yo[a] = y[a];
+            }
+          }
+        }
+      }
+      __syncthreads();
+      lap(17);
+      double dot = 0;
+      if (on) {
+        double ysum = 0;
+        for (int t = 0; t < ypn; t++) ysum += yp[(size_t)(yp0 + t) * 6 + row];
+        double vv = 0;
+        {
+          double va = 0, vb = 0;   // (three independent chains)
+          const double* po = sP + slot * kBlockDim + (u / 6) * 6;
+#pragma unroll
+          for (int cc = 0; cc < 6; cc++) vv += trow[cc] * po[cc];
+          if (nf > 0) {
+            const bool here = (oth0 / kBlockPoses) == k;
+#pragma unroll
+            for (int cc = 0; cc < 6; cc++)
+              va += trow[6 + cc] * (here ? sP[slot * kBlockDim + (oth0 - k * kBlockPoses) * 6 + cc] : ldc(pvec + (size_t)oth0 * 6 + cc));
+          }
+          if (nf > 1) {
+            const bool here = (oth1 / kBlockPoses) == k;
+#pragma unroll
+            for (int cc = 0; cc < 6; cc++)
+              vb += trow[12 + cc] * (here ? sP[slot * kBlockDim + (oth1 - k * kBlockPoses) * 6 + cc] : ldc(pvec + (size_t)oth1 * 6 + cc));
+          }
+          vv += va + vb;
+          for (int kk = nr.x; kk < nr.y; kk++) {   // further pose-pose factors of this pose (loop closures): generic list
+            const int inc = G.pinc[kk], f = inc >> 1, side = inc & 1;
+            const int j = G.pf_j[f];
+            if (j < 0) continue;
+            const int ot = side ? G.pf_i[f] : j;
+            const double* A12 = G.PF + (size_t)f * 120 + 72;
+            for (int cc = 0; cc < 6; cc++) {
+              const double a = side ? ldc(A12 + cc * 6 + row) : ldc(A12 + row * 6 + cc);
+              vv += a * ldc(pvec + (size_t)ot * 6 + cc);
+            }
+          }
+        }
+        q_u = vv - ysum;
+        dot = p_u * q_u;
+      }
+      lap1(6);
+      if (live) sR[slot * kBlockDim + u] = on ? q_u : 0.0;
+      __syncthreads();
+      if (live) restrict_block(sR, slot, u, k, np, G.qcpart);
+      lap(18);
+      const double pq = team_reduce_flag(c, dot);
+      tmr.lap(19);
+      if (!(pq > 0.0)) break;
+      const double alpha = rz / pq;
+      // ================= C =================
+      const double* rc_old = G.rcpart[rcb];
+      double* rc_new = G.rcpart[rcb ^ 1];
+      for (int i0 = tid; i0 < ldm; i0 += 4 * kThreads) {
+        double va[4][2], vq[4][2];
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const int i = i0 + m * kThreads, node = i / 6, rr = i - node * 6;
+#pragma unroll
+          for (int side = 0; side < 2; side++) {
+            const int kb = node - side;
+            const bool ok = (i < ldm) && (kb >= 0) && (kb < G.nblk);
+            va[m][side] = ok ? ldc(rc_old + (size_t)kb * 12 + side * 6 + rr) : 0.0;
+            vq[m][side] = ok ? ldc(G.qcpart + (size_t)kb * 12 + side * 6 + rr) : 0.0;
+          }
+        }
+#pragma unroll
+        for (int m = 0; m < 4; m++) {
+          const int i = i0 + m * kThreads;
+          if (i < ldm) src[i] = (0.0 + (va[m][0] - alpha * vq[m][0])) + (va[m][1] - alpha * vq[m][1]);
+        }
+      }
+      if (on) { x_u += alpha * p_u; r_u -= alpha * q_u; }
+      if (live) sR[slot * kBlockDim + u] = on ? r_u : 0.0;
+      __syncthreads();
+      lap(13);
+      if (live) restrict_block(sR, slot, u, k, np, rc_new);
+      dot = 0;
+      {
+        const int nw = nwarp_team();
+        for (int i = warp_team(); i < ldm; i += nw) {
+          const double* arow = Ai + ac_index(G.ldmc, i, 0);
+          double acc = 0;
+          int j = 2 * lane;
+          for (; j + 64 * 15 < ldm; j += 64 * 16) {
+            double2 av[16];
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+              const int jj = j + 64 * t;
+              av[t] = __ldcg(reinterpret_cast<const double2*>(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk)));
+            }
+#pragma unroll
+            for (int t = 0; t < 16; t++) acc += av[t].x * src[j + 64 * t] + av[t].y * src[j + 64 * t + 1];
+          }
+          {
+            double2 av[16];
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+              const int jj = j + 64 * t;
+              av[t] = (jj < ldm) ? __ldcg(reinterpret_cast<const double2*>(arow + (size_t)(jj / kGjChunk) * kGjTile + (jj % kGjChunk))) : make_double2(0.0, 0.0);
+            }
+#pragma unroll
+            for (int t = 0; t < 16; t++) {
+              const int jj = j + 64 * t;
+              if (jj < ldm) acc += av[t].x * src[jj] + av[t].y * src[jj + 1];
+            }
+          }
+          acc = warp_sum(acc);
+          if (lane == 0) { G.zc[i] = acc; dot += src[i] * acc; }
+        }
+      }
+      lap(14);
+      {
+        // z = Binv r of every owned block: four threads per row of the symmetric block (interleaved columns, fixed-order
+        // combination by two shuffles); column part j < u reads element (j, u), row part j >= u element (u, j) of the packed
+        // upper triangle.  The thread that owns row u in the loop state picks its value up from shared memory.
+        double* sZ = sE;   // (scratch of the slot: free in phase C)  [96]
+        for (int s = 0; s < nown; s++) {
+          if (tid < 4 * kBlockDim) {
+            const int uu = tid >> 2, qq = tid & 3;
+            const double* cb = reinterpret_cast<const double*>(g_smem + L.slot0 + s * L.stride + L.o_B);
+            const double* rv = sR + s * kBlockDim;
+            double z0 = 0, z1 = 0;
+            for (int j = qq; j < uu; j += 4) z0 += cb[j * kBlockDim - (j * (j - 1)) / 2 + (uu - j)] * rv[j];
+            const double* cu = cb + uu * kBlockDim - (uu * (uu - 1)) / 2 - uu;
+            for (int j = uu + ((qq - uu) & 3); j < kBlockDim; j += 4) z1 += cu[j] * rv[j];
+            double zl = z0 + z1;
+            zl += __shfl_xor_sync(0xffffffffu, zl, 1);
+            zl += __shfl_xor_sync(0xffffffffu, zl, 2);
+            if (qq == 0) reinterpret_cast<double*>(g_smem + L.slot0 + s * L.stride)[uu] = zl;
+          }
+        }
+        __syncthreads();
+        if (on) { z_u = sZ[u]; dot += r_u * z_u; }
+      }
+      lap(15);
+      const double rz_new = team_reduce_flag(c, dot);
+      tmr.lap(20);
+      rcb ^= 1;
+      it++;
+      if (!(rz_new > tol2 * rz0)) break;
+      beta = rz_new / rz;
+      rz = rz_new;
+    }
+    if (on) G.x[o] = x_u;
+    team_barrier(c);
+    return it;
   }
 
   // -------- spanning solves: the owners publish the final x to every rank (during the iteration x is owner-only) ----
