@@ -11,6 +11,7 @@ __device__ void linearize(Phase& ph, Ctx& c) {
   team_barrier(c);
   ph.lap2(22);
   ph.assemble();
+  if (G.n_asplit > 0) { team_barrier(c); ph.assemble_split(); }
   team_barrier(c);
   ph.lap2(23);
 }
@@ -85,6 +86,7 @@ __device__ double schur_solve(Phase& ph, Ctx& c, double lambda, int acinv, int* 
   if (rz0 > 0.0 && !done && resident) {
     it = ph.pcg_resident(lambda, acinv, rcb, rz0, rz, tol2, ft);
   } else if (rz0 > 0.0 && !done) {
+    c.light = c.mirror ? 0 : 1;   // every value the loop exchanges between CTAs is read through L2 (ld.global.cg / bulk copies)
     while (it < G.prm.pcg_max_iter) {
       ft.sync();
       ph.update_direction(cur, beta);
@@ -114,6 +116,7 @@ __device__ double schur_solve(Phase& ph, Ctx& c, double lambda, int acinv, int* 
       rz = rz_new;
       cur ^= 1;
     }
+    c.light = 0;
   }
   *its = it;
   // planes: dl = Hll_d^-1 (-gl - W^T x)
@@ -338,6 +341,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
   c.span_w = 1; c.span_r = 0; c.mirror = 0; c.gbar = nullptr; c.gbar_target = 0;
   c.rflag = reinterpret_cast<unsigned long long*>(bars + 8192) + (size_t)team * team_ctas * 4;
   c.red_seq = 0;
+  c.light = 0;
   if (threadIdx.x == 0) {
     unsigned long long* gbar = reinterpret_cast<unsigned long long*>(smem + kSmGjBar);
     mbar_init(gbar, 1);

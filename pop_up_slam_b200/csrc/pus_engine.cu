@@ -230,7 +230,8 @@ static int upload(Solver* s) {
     d.n_heavy = c.n_heavy; d.n_huge = c.n_huge;
     UP(pf_i); UP(pf_j); UP(pinc_ptr); UP(pinc); UP(pnbr); UP(pf_meas); UP(pf_sinf);
     UP(lp_plane); UP(linc_ptr); UP(linc); UP(lp_meas); UP(lp_sinf);
-    UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple); UP(grp_info); UP(grp_info2);
+    UP(blk_grp_ptr); UP(grp_plane); UP(grp_mem_ptr); UP(grp_mem); UP(blk_simple); UP(grp_info); UP(grp_info2); UP(at_plane); UP(at_lo); UP(at_hi); UP(at_ptr); UP(as_plane);
+    d.n_atask = c.n_atask; d.n_asplit = c.n_asplit;
     d.res_nt = c.res_nt; d.res_ng = c.res_ng; d.res_np = c.res_np;
     UP(ce_ptr); UP(ce_node); UP(ce_plane); UP(ce_lo); UP(ce_hi); UP(n2ce_ptr); UP(n2ce);
     UP(hv_plane); UP(lp_ptr); UP(lp_cea); UP(lp_ceb); UP(fp_ptr); UP(fp_f);
@@ -245,7 +246,7 @@ static int upload(Solver* s) {
     AL(W, T * kWStride, "Wtiles"); AL(Wt, TL * kWStride, "Wttiles"); AL(JP, E * 21, "JP"); AL(JL, E * 12, "JL");
     AL(PF, (size_t)c.Epf * 120, "PF"); AL(LP, (size_t)c.Elp * 12, "LP");
     AL(Hpp, N * 36, "Hpp"); AL(gp, N * 6, "gp"); AL(Hll, M * 9, "Hll"); AL(gl, M * 3, "gl"); AL(Hinv, M * 9, "Hinv");
-    AL(ypart, 8, "ypart"); AL(upartb, (size_t)std::max(1, c.ngrp) * 3, "upartb");
+    AL(ypart, 8, "ypart"); AL(upartb, (size_t)std::max(1, c.ngrp) * 3, "upartb"); AL(hpart, (size_t)std::max(1, c.n_atask) * 9, "hpart");
     AL(Binv, (size_t)c.nblk * kPackedBlock, "Binv"); AL(Wc, (size_t)c.nce * 18, "Wc"); AL(Yc, (size_t)c.nce * 18, "Yc");
     AL(Ac[0], ac_doubles(6 * c.nc_pad), "Ac0"); AL(Ac[1], ac_doubles(6 * c.nc_pad), "Ac1");
     AL(Wc2, (size_t)c.nce2 * 18, "Wc2"); AL(Yc2, (size_t)c.nce2 * 18, "Yc2"); AL(D2inv, (size_t)c.ng2 * kBlockDim * kBlockDim, "D2inv");

@@ -42,6 +42,7 @@ constexpr int kTile = 32;                  // edges per warp tile
 constexpr int kWStride = 18 * kTile;       // doubles per W tile
 constexpr int kMaxGrp = 256;               // plane groups per 16-pose block held in shared memory
 constexpr int kMaxPart = 64;               // (tile, pose) partial sums per block held in shared memory
+constexpr int kAsmChunk = 128;             // plane-major edge slots per Hll / gl assembly task (one warp)
 
 struct HNode {
   int kind = NODE_POSE;
@@ -202,6 +203,10 @@ struct Compiled {
   // res_* = largest tile / group / (tile, pose)-run count of any pose block (uniform shared-memory strides)
   std::vector<int> grp_info2;
   int res_nt = 0, res_ng = 0, res_np = 0;
+  // Hll / gl assembly tasks: the plane-major slots of every plane cut into chunks of kAsmChunk (a plane seen from thousands of
+  // poses is gathered by many warps instead of one); at_* per task, at_ptr per plane, as_plane = planes with more than one task
+  std::vector<int> at_plane, at_lo, at_hi, at_ptr, as_plane;
+  int n_atask = 0, n_asplit = 0;
   // coarse (hat) space: (plane, coarse node) pairs
   std::vector<int> ce_ptr, ce_node, ce_plane, ce_lo, ce_hi, n2ce_ptr, n2ce;
   std::vector<int> hv_plane, lp_ptr, lp_cea, lp_ceb, fp_ptr, fp_f;   // coarse assembly: heavy planes, per node-pair lists
@@ -369,6 +374,25 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     if (c.heavy.empty()) c.heavy.push_back(-1);
     if (c.huge.empty()) c.huge.push_back(-1);
   }
+  // ---- Hll / gl assembly tasks ----
+  c.at_plane.clear(); c.at_lo.clear(); c.at_hi.clear(); c.as_plane.clear();
+  c.at_ptr.assign(M + 1, 0);
+  for (int l = 0; l < M; l++) {
+    const int s0 = c.pl_ptr[l], s1 = c.pl_ptr[l + 1];
+    c.at_ptr[l] = (int)c.at_plane.size();
+    int lo = s0;
+    do {   // (a plane without edges still gets one empty task: its priors are added there)
+      const int hi = std::min(s1, lo + kAsmChunk);
+      c.at_plane.push_back(l); c.at_lo.push_back(lo); c.at_hi.push_back(hi);
+      lo = hi;
+    } while (lo < s1);
+    if ((int)c.at_plane.size() - c.at_ptr[l] > 1) c.as_plane.push_back(l);
+  }
+  c.at_ptr[M] = (int)c.at_plane.size();
+  c.n_atask = (int)c.at_plane.size();
+  c.n_asplit = (int)c.as_plane.size();
+  if (c.at_plane.empty()) { c.at_plane.push_back(0); c.at_lo.push_back(0); c.at_hi.push_back(0); }
+  if (c.as_plane.empty()) c.as_plane.push_back(-1);
   // ---- incidence lists ----
   c.pinc_ptr.assign(N + 1, 0);
   for (int f = 0; f < c.Epf; f++) { c.pinc_ptr[c.pf_i[f] + 1]++; if (c.pf_j[f] >= 0) c.pinc_ptr[c.pf_j[f] + 1]++; }

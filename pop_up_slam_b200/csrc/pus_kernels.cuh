@@ -88,6 +88,9 @@ struct DevGraph {
   const int* grp_info2;         // block-resident PCG: {plane, first per-block partial, number of partials, own slot} per group
   int res_nt, res_ng, res_np;   // largest tile / group / (tile, pose)-run count of any pose block
   double* upartb;               // [ngrp][3] per-(block, plane) partial sums of W^T p
+  const int *at_plane, *at_lo, *at_hi, *at_ptr, *as_plane;   // Hll / gl assembly tasks (chunks of a plane's edges), split planes
+  int n_atask, n_asplit;
+  double* hpart;                // [n_atask][9] partial sums of the split planes
   const int *ce_ptr, *ce_node, *ce_plane, *ce_lo, *ce_hi, *n2ce_ptr, *n2ce;
   const int *hv_plane, *lp_ptr, *lp_cea, *lp_ceb, *fp_ptr, *fp_f;
   int n_hv;
@@ -141,6 +144,7 @@ struct Ctx {
   unsigned char* smem;   // dynamic shared memory
   unsigned long long* rflag;   // flag-stamped reduction slots of this team ([2 sets][tsize][2 words], zeroed by the host per launch)
   unsigned red_seq;      // sequence number of the last flag-stamped reduction (same on every thread of the team)
+  int light;             // 1: team_barrier() / team_reduce<1>() use the fence-free barrier and the flag-stamped reduction
 };
 
 __device__ __forceinline__ double ldc(const double* p) { return __ldcg(p); }
@@ -164,10 +168,33 @@ __device__ __forceinline__ unsigned ld_acquire_sys_u32(const unsigned* p) {
   return v;
 }
 
+// Team barrier for the PCG loops, without the L1 invalidation that a gpu-scope fence or an acquire load implies (CCTL.IVALL
+// throws away every cached local-memory line of the SM -- the spilled loop state -- three times per PCG iteration).  Release
+// side: one release-reduction (orders the CTA's prior writes, through the CTA barrier, before the arrival).  Wait side:
+// relaxed polling; every value another CTA wrote is read with ld.global.cg (L2) inside those loops, so nothing stale in L1 can
+// be observed.  The full team_barrier() (fence + invalidate) brackets the loops.
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void team_barrier_light(Ctx& c) {
+  __syncthreads();
+  if (c.tsize > 1) {
+    if (threadIdx.x == 0) {
+      c.bar_target += (unsigned)c.tsize;
+      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.bar), "r"(1u) : "memory");
+      while ((int)(ld_relaxed_u32(c.bar) - c.bar_target) < 0) { }
+    }
+    __syncthreads();
+  }
+}
+
 // All CTAs of the team must call this the same number of times.  In the global view of a spanning solve the barrier
 // covers the CTAs of every rank: each CTA adds one to its own rank's counter and to every peer's (system-scope
 // atomics through peer-mapped memory), and waits for its own counter.
 __device__ __forceinline__ void team_barrier(Ctx& c) {
+  if (c.light) { team_barrier_light(c); return; }   // inside the single-GPU PCG loops (set / cleared by schur_solve)
   __syncthreads();
 #ifndef PUS_NO_SPAN
   if (c.mirror) {
@@ -199,28 +226,6 @@ __device__ __forceinline__ void team_barrier(Ctx& c) {
   }
 }
 
-
-// Team barrier for the PCG loops, without the L1 invalidation that a gpu-scope fence or an acquire load implies (CCTL.IVALL
-// throws away every cached local-memory line of the SM -- the spilled loop state -- three times per PCG iteration).  Release
-// side: one release-reduction (orders the CTA's prior writes, through the CTA barrier, before the arrival).  Wait side:
-// relaxed polling; every value another CTA wrote is read with ld.global.cg (L2) inside those loops, so nothing stale in L1 can
-// be observed.  The full team_barrier() (fence + invalidate) brackets the loops.
-__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
-  unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ void team_barrier_light(Ctx& c) {
-  __syncthreads();
-  if (c.tsize > 1) {
-    if (threadIdx.x == 0) {
-      c.bar_target += (unsigned)c.tsize;
-      asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(c.bar), "r"(1u) : "memory");
-      while ((int)(ld_relaxed_u32(c.bar) - c.bar_target) < 0) { }
-    }
-    __syncthreads();
-  }
-}
 
 // store to a PCG vector that every rank keeps a full copy of (no-op distinction outside the spanning global view)
 template <typename T>
@@ -372,7 +377,7 @@ __host__ __device__ inline ResLay res_layout(int nt, int ng, int np, int ldm, in
   L.src = L.sR + nown * kBlockDim * 8;
   L.slot0 = L.src + r16(ldm * 8);
   const int ua = nt * 32 * 24, ub = r16(ng * 24) + np * 48;
-  const int uc = kBlockDim * 8;   // phase C: z of the block
+  const int uc = 6 * kBlockDim * 8;   // phase C: row sums and up to five warps' column partials of z = Binv r
   L.o_ei = r16(ua > ub ? (ua > uc ? ua : uc) : (ub > uc ? ub : uc));
   L.o_gi = L.o_ei + nt * 128;
   L.o_gm = L.o_gi + ng * 16;
@@ -387,8 +392,10 @@ __host__ __device__ inline ResLay res_layout(int nt, int ng, int np, int ldm, in
 // deterministic team-wide sum of K (<= 4) values; result broadcast to every thread.
 // warp partials -> CTA partial (warp 0) -> global slot -> team barrier -> every CTA's warp 0 sums the
 // per-CTA partials with strided lanes + a shuffle tree (fixed order, so all CTAs get identical bits).
+__device__ __forceinline__ double team_reduce_flag(Ctx& c, double v);
 template <int K>
 __device__ __forceinline__ void team_reduce(Ctx& c, double* red, double* v) {
+  if (K == 1 && c.light) { v[0] = team_reduce_flag(c, v[0]); return; }
   double* s = reinterpret_cast<double*>(g_smem + kSmRed);
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 #pragma unroll
@@ -795,10 +802,13 @@ struct Phase {
       }
     }
     const int lane = threadIdx.x & 31;
-    for (int l = warp_team(); l < G.M; l += nwarp_team()) {
+    // Hll / gl: a warp per task = chunk of at most kAsmChunk edges of one plane; a plane with a single task is finished here, the
+    // others (the ground plane is seen from every pose) leave partial sums for assemble_split()
+    for (int t = warp_team(); t < G.n_atask; t += nwarp_team()) {
+      const int l = G.at_plane[t];
       double h[9];
       for (int k = 0; k < 9; k++) h[k] = 0;  // 0..5: Hll upper (00,01,02,11,12,22); 6..8: gl
-      for (int s = G.pl_ptr[l] + lane; s < G.pl_ptr[l + 1]; s += 32) {
+      for (int s = G.at_lo[t] + lane; s < G.at_hi[t]; s += 32) {
         const double* jl = G.JL + (size_t)G.pl2pm[s] * 12;
         double J[12];
         for (int k = 0; k < 12; k++) J[k] = ldc(jl + k);
@@ -813,17 +823,36 @@ struct Phase {
         h[8] += J[2] * J[9] + J[5] * J[10] + J[8] * J[11];
       }
       for (int k = 0; k < 9; k++) h[k] = warp_sum(h[k]);
-      if (lane == 0) {
-        double H[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
-        double gg[3] = {h[6], h[7], h[8]};
-        for (int k = G.linc_ptr[l]; k < G.linc_ptr[l + 1]; k++) {
-          const double* o = G.LP + (size_t)G.linc[k] * 12;
-          for (int t = 0; t < 9; t++) H[t] += ldc(o + t);
-          for (int t = 0; t < 3; t++) gg[t] += ldc(o + 9 + t);
-        }
-        for (int t = 0; t < 9; t++) G.Hll[(size_t)l * 9 + t] = H[t];
-        for (int t = 0; t < 3; t++) G.gl[(size_t)l * 3 + t] = gg[t];
+      if (G.at_ptr[l + 1] - G.at_ptr[l] > 1) {
+        if (lane == 0) for (int k = 0; k < 9; k++) G.hpart[(size_t)t * 9 + k] = h[k];
+      } else if (lane == 0) {
+        finish_plane(l, h);
       }
+    }
+  }
+  __device__ __forceinline__ void finish_plane(int l, const double* h) {
+    double H[9] = {h[0], h[1], h[2], h[1], h[3], h[4], h[2], h[4], h[5]};
+    double gg[3] = {h[6], h[7], h[8]};
+    for (int k = G.linc_ptr[l]; k < G.linc_ptr[l + 1]; k++) {
+      const double* o = G.LP + (size_t)G.linc[k] * 12;
+      for (int t = 0; t < 9; t++) H[t] += ldc(o + t);
+      for (int t = 0; t < 3; t++) gg[t] += ldc(o + 9 + t);
+    }
+    for (int t = 0; t < 9; t++) G.Hll[(size_t)l * 9 + t] = H[t];
+    for (int t = 0; t < 3; t++) G.gl[(size_t)l * 3 + t] = gg[t];
+  }
+  // second stage for the planes whose edges were gathered by several warps: a warp per plane adds the tasks' partial sums
+  // (lane-strided, then the shuffle tree: fixed order) -- behind a team barrier after assemble()
+  __device__ void assemble_split() {
+    const int lane = threadIdx.x & 31;
+    for (int q = warp_team(); q < G.n_asplit; q += nwarp_team()) {
+      const int l = G.as_plane[q];
+      double h[9];
+      for (int k = 0; k < 9; k++) h[k] = 0;
+      for (int t = G.at_ptr[l] + lane; t < G.at_ptr[l + 1]; t += 32)
+        for (int k = 0; k < 9; k++) h[k] += ldc(G.hpart + (size_t)t * 9 + k);
+      for (int k = 0; k < 9; k++) h[k] = warp_sum(h[k]);
+      if (lane == 0) finish_plane(l, h);
     }
   }
 
@@ -2411,9 +2440,16 @@ struct Phase {
         for (int g = u; g < ng; g += kBlockDim) {
           const int2 m = gm[g];
           double s0 = 0, s1 = 0, s2 = 0;
-          for (int i = 0; i < m.y; i++) {
-            const double* se = sE + (size_t)mem[m.x + i] * 3;
-            s0 += se[0]; s1 += se[1]; s2 += se[2];
+          for (int i = 0; i < m.y; i += 4) {   // (four members per round: their loads are independent; fixed summation order)
+            double e4[4][3];
+#pragma unroll
+            for (int q = 0; q < 4; q++) {
+              const double* se = sE + (size_t)mem[m.x + min(i + q, m.y - 1)] * 3;
+              const bool ok = i + q < m.y;
+              e4[q][0] = ok ? se[0] : 0.0; e4[q][1] = ok ? se[1] : 0.0; e4[q][2] = ok ? se[2] : 0.0;
+            }
+#pragma unroll
+            for (int q = 0; q < 4; q++) { s0 += e4[q][0]; s1 += e4[q][1]; s2 += e4[q][2]; }
           }
           double* uo = G.upartb + (size_t)gi[g].w * 3;
           uo[0] = s0; uo[1] = s1; uo[2] = s2;
@@ -2465,7 +2501,6 @@ struct Phase {
                                ldc(G.Hinv + (size_t)l * 9 + lane * 3 + 2) * uu[2];
         }
       }
-      lap1(22);
       // listed heavy planes: `wpe` warps each, every warp one contiguous chunk of the plane's per-block partials
       double hHi[9];
       int hidx = -1, hg = -1;
@@ -2496,7 +2531,6 @@ struct Phase {
         for (int b = 0; b < 3; b++) uu[b] = warp_sum(uu[b]);
         if (lane < 3) hvp[(h * kWarps + j) * 3 + lane] = (lane == 0) ? uu[0] : (lane == 1 ? uu[1] : uu[2]);
       }
-      lap1(23);
       if (nh) {
         __syncthreads();
         if (hidx >= 0) {
@@ -2585,7 +2619,6 @@ struct Phase {
         q_u = vv - ysum;
         dot = p_u * q_u;
       }
-      lap1(6);
       if (live) sR[slot * kBlockDim + u] = on ? q_u : 0.0;
       __syncthreads();
       if (live) restrict_block(sR, slot, u, k, np, G.qcpart);
@@ -2623,8 +2656,13 @@ struct Phase {
       if (live) restrict_block(sR, slot, u, k, np, rc_new);
       dot = 0;
       {
-        const int nw = nwarp_team();
-        for (int i = warp_team(); i < ldm; i += nw) {
+        // rows of A_c^-1, one per warp: when the CTAs that own one pose block fewer than the others have enough warps for all
+        // the rows, only they take rows (warp-major interleave), so the CTAs with the extra block are not the last to arrive
+        const int n3 = G.nblk % c.tsize, ne = c.tsize - n3;
+        const bool bal = n3 > 0 && ne * kWarps >= ldm;
+        const int nw = bal ? ne * kWarps : nwarp_team();
+        const int w0 = bal ? (c.rank >= n3 ? warp * ne + (c.rank - n3) : ldm) : warp_team();
+        for (int i = w0; i < ldm; i += nw) {
           const double* arow = Ai + ac_index(G.ldmc, i, 0);
           double acc = 0;
           int j = 2 * lane;
@@ -2657,27 +2695,77 @@ struct Phase {
       }
       lap(14);
       {
-        // z = Binv r of every owned block: four threads per row of the symmetric block (interleaved columns, fixed-order
-        // combination by two shuffles); column part j < u reads element (j, u), row part j >= u element (u, j) of the packed
-        // upper triangle.  The thread that owns row u in the loop state picks its value up from shared memory.
-        double* sZ = sE;   // (scratch of the slot: free in phase C)  [96]
-        for (int s = 0; s < nown; s++) {
-          if (tid < 4 * kBlockDim) {
-            const int uu = tid >> 2, qq = tid & 3;
-            const double* cb = reinterpret_cast<const double*>(g_smem + L.slot0 + s * L.stride + L.o_B);
-            const double* rv = sR + s * kBlockDim;
-            double z0 = 0, z1 = 0;
-            for (int j = qq; j < uu; j += 4) z0 += cb[j * kBlockDim - (j * (j - 1)) / 2 + (uu - j)] * rv[j];
-            const double* cu = cb + uu * kBlockDim - (uu * (uu - 1)) / 2 - uu;
-            for (int j = uu + ((qq - uu) & 3); j < kBlockDim; j += 4) z1 += cu[j] * rv[j];
-            double zl = z0 + z1;
-            zl += __shfl_xor_sync(0xffffffffu, zl, 1);
-            zl += __shfl_xor_sync(0xffffffffu, zl, 2);
-            if (qq == 0) reinterpret_cast<double*>(g_smem + L.slot0 + s * L.stride)[uu] = zl;
+        // z = Binv r of every owned block, every element of the packed upper triangle read ONCE and conflict-free: up to five
+        // warps per block, a warp takes rows i = wi, wi + wps, ...; lanes are columns j = lane + 32 m.  Element (i, j), j > i,
+        // feeds z_i (b * r_j, summed across the lanes: eight rows per shuffle tree) and z_j (b * r_i, accumulated per lane, one
+        // partial per warp); the owner thread of a row adds the row sum and the warps' column partials in a fixed order.
+        const int wps = min(5, kWarps / max(nown, 1));   // (a CTA of a wide team may own no block at all)
+        const int ws = warp / wps, wi = warp - ws * wps;
+        if (ws < nown) {
+          unsigned char* sbs = g_smem + L.slot0 + ws * L.stride;
+          const double* cb = reinterpret_cast<const double*>(sbs + L.o_B);
+          const double* rv = sR + ws * kBlockDim;
+          double* zrow = reinterpret_cast<double*>(sbs);
+          const double rj0 = rv[lane], rj1 = rv[lane + 32], rj2 = rv[lane + 64];
+          double c0 = 0, c1 = 0, c2 = 0;
+          for (int ib = wi; ib < kBlockDim; ib += 8 * wps) {
+            // (branch-free: all loads of the batch are issued before the first use; rows past the end re-read row 95 with
+            // zero weights, columns left of the diagonal re-read earlier rows' entries and are masked)
+            double ra[8], bv[8][3], rr[8];
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+              const int i = min(ib + wps * t, kBlockDim - 1);
+              const double* rowp = cb + i * kBlockDim - (i * (i - 1)) / 2 - i;   // element (i, j) at rowp[j], j >= i
+              rr[t] = rv[i];
+              bv[t][0] = rowp[lane]; bv[t][1] = rowp[min(lane + 32, kBlockDim - 1)]; bv[t][2] = rowp[min(lane + 64, kBlockDim - 1)];
+            }
+#pragma unroll
+            for (int t = 0; t < 8; t++) {
+              const int i = ib + wps * t;
+              const bool ok = i < kBlockDim;
+              const double b0 = (ok && lane >= i) ? bv[t][0] : 0.0, b1 = (ok && lane + 32 >= i) ? bv[t][1] : 0.0,
+                           b2 = (ok && lane + 64 >= i) ? bv[t][2] : 0.0;
+              ra[t] = b0 * rj0 + b1 * rj1 + b2 * rj2;
+              const double ri = rr[t];
+              c0 += (lane == i) ? 0.0 : b0 * ri;
+              c1 += (lane + 32 == i) ? 0.0 : b1 * ri;
+              c2 += (lane + 64 == i) ? 0.0 : b2 * ri;
+            }
+#pragma unroll
+            for (int t = 0; t < 4; t++) {
+              const bool hi = (lane & 16) != 0;
+              const double keep = hi ? ra[t + 4] : ra[t], send = hi ? ra[t] : ra[t + 4];
+              ra[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+            }
+#pragma unroll
+            for (int t = 0; t < 2; t++) {
+              const bool hi = (lane & 8) != 0;
+              const double keep = hi ? ra[t + 2] : ra[t], send = hi ? ra[t] : ra[t + 2];
+              ra[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+            }
+            {
+              const bool hi = (lane & 4) != 0;
+              const double keep = hi ? ra[1] : ra[0], send = hi ? ra[0] : ra[1];
+              ra[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+            }
+            ra[0] += __shfl_xor_sync(0xffffffffu, ra[0], 2);
+            ra[0] += __shfl_xor_sync(0xffffffffu, ra[0], 1);
+            const int i = ib + wps * (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
+            if ((lane & 3) == 0 && i < kBlockDim) zrow[i] = ra[0];
           }
+          double* colp = zrow + kBlockDim + wi * kBlockDim;
+          colp[lane] = c0; colp[lane + 32] = c1; colp[lane + 64] = c2;
         }
+        lap1(22);
         __syncthreads();
-        if (on) { z_u = sZ[u]; dot += r_u * z_u; }
+        lap1(23);
+        if (on) {
+          const double* zr = sE;
+          double zl = zr[u];
+          for (int w = 0; w < wps; w++) zl += zr[kBlockDim + w * kBlockDim + u];
+          z_u = zl;
+          dot += r_u * zl;
+        }
       }
       lap(15);
       const double rz_new = team_reduce_flag(c, dot);

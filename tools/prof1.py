@@ -21,7 +21,7 @@ st = a.stats()
 ph = st['phase_ms']
 print("prec builds", round(st["phase_ms"][5]), end=" | ")
 print("cfg", cfg, g.dims(), "iters", it, "pcg", st['pcg_iterations'], "kernel_ms %.2f"%st['kernel_ms'], "ctas", st['grid_ctas'])
-names = {0:'linearize',1:'setup',2:'pcg',3:'update',4:'chi2',8:'s.Hinv',9:'s.blocks',10:'s.Wc',11:'s.Ac',12:'s.AcInv',16:'p.sweepPl',17:'r.tiles',18:'r.side',19:'p.poseRed',20:'p.precRed',21:'p.pose.vg',22:'r.vg.direct',23:'r.vg.hvload',6:'r.side.own',13:'p.prec.rc',14:'p.prec.coarse',15:'p.prec.blocks'}
+names = {0:'linearize',1:'setup',2:'pcg',3:'update',4:'chi2',8:'s.Hinv',9:'s.blocks',10:'s.Wc',11:'s.Ac',12:'s.AcInv',16:'p.sweepPl',17:'r.tiles',18:'r.side',19:'p.poseRed',20:'p.precRed',21:'p.pose.vg',22:'probe.22',23:'probe.23',6:'probe.6',13:'p.prec.rc',14:'p.prec.coarse',15:'p.prec.blocks'}
 nset = st['lm_iterations']+1
 for k,n in names.items():
     per = ph[k]/nset*1e3 if (k<13) else ph[k]/max(1,st['pcg_iterations'])*1e3
