@@ -665,7 +665,7 @@ struct Phase {
   __device__ Phase(Ctx& cc) : c(cc) {}
   __device__ __forceinline__ void lap(int slot) { if (ft) ft->lap(slot); }
   // slots 6 / 22 / 23 are shared: sub-stages of the resident PCG loop (fine_timers == 1) or of linearize (fine_timers == 2)
-  __device__ __forceinline__ void lap1(int slot) { if (ft && G.prm.fine_timers == 1) ft->lap(slot); }
+  __device__ __forceinline__ void lap1(int slot) { if (ft && (G.prm.fine_timers & 1)) ft->lap(slot); }
   __device__ __forceinline__ void lap2(int slot) { if (ft && G.prm.fine_timers == 2) ft->lap(slot); }
 
   __device__ __forceinline__ int tid_team() const { return c.rank * kThreads + threadIdx.x; }
@@ -724,33 +724,55 @@ struct Phase {
 
   // -------- linearise: pose priors / odometry, plane priors --------
   __device__ void lin_other() {
-    for (int f = tid_team(); f < G.Epf; f += nthr_team()) {
-      int i = G.pf_i[f], j = G.pf_j[f];
-      double p1[7], p2[7], m[6], si[21];
-      for (int t = 0; t < 7; t++) p1[t] = ldc(G.pose_lin + (size_t)i * 7 + t);
-      if (j >= 0) for (int t = 0; t < 7; t++) p2[t] = ldc(G.pose_lin + (size_t)j * 7 + t);
-      for (int t = 0; t < 6; t++) m[t] = G.pf_meas[(size_t)f * 6 + t];
-      for (int t = 0; t < 21; t++) si[t] = G.pf_sinf[(size_t)f * 21 + t];
-      double r[6], J1[36], J2[36];
-      for (int t = 0; t < 36; t++) J2[t] = 0;
-      if (G.prm.jac_numeric) pose_factor_numeric_dev(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
-      else pose_factor_linearize(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
-      double* o = G.PF + (size_t)f * 120;
-      for (int a = 0; a < 6; a++)
-        for (int b = 0; b < 6; b++) {
-          double s11 = 0, s22 = 0, s12 = 0;
-          for (int k = 0; k < 6; k++) {
-            s11 += J1[k * 6 + a] * J1[k * 6 + b];
-            s22 += J2[k * 6 + a] * J2[k * 6 + b];
-            s12 += J1[k * 6 + a] * J2[k * 6 + b];
-          }
-          o[a * 6 + b] = s11; o[36 + a * 6 + b] = s22; o[72 + a * 6 + b] = s12;
+    // Pose factors in chunks of 32, one chunk per CTA at a time: warp 0 evaluates residual and Jacobians (a lane per factor) and
+    // leaves them in shared memory; the whole CTA then forms the 120 products per factor (J1^T J1, J2^T J2, J1^T J2, J1^T r,
+    // J2^T r) -- a thread per output, coalesced stores -- instead of 650 dependent multiply-adds over local-memory arrays in the
+    // one thread that owns the factor (graphs have few pose factors: that thread was the whole phase).
+    {
+      constexpr int LDJ = 79;   // J1[36] J2[36] r[6], odd stride
+      double* sJ = reinterpret_cast<double*>(g_smem + kSmWork);
+      const int tid = threadIdx.x, lane = tid & 31;
+      const int nchunk = (G.Epf + 31) / 32;
+      for (int ch = c.rank; ch < nchunk; ch += c.tsize) {
+        const int f0 = ch * 32, nf = min(32, G.Epf - f0);
+        __syncthreads();
+        if (tid < 32 && lane < nf) {
+          const int f = f0 + lane;
+          const int i = G.pf_i[f], j = G.pf_j[f];
+          double p1[7], p2[7], m[6], si[21];
+          for (int t = 0; t < 7; t++) p1[t] = ldc(G.pose_lin + (size_t)i * 7 + t);
+          if (j >= 0) for (int t = 0; t < 7; t++) p2[t] = ldc(G.pose_lin + (size_t)j * 7 + t);
+          for (int t = 0; t < 6; t++) m[t] = G.pf_meas[(size_t)f * 6 + t];
+          for (int t = 0; t < 21; t++) si[t] = G.pf_sinf[(size_t)f * 21 + t];
+          double r[6], J1[36], J2[36];
+          for (int t = 0; t < 36; t++) J2[t] = 0;
+          if (G.prm.jac_numeric) pose_factor_numeric_dev(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
+          else pose_factor_linearize(p1, j >= 0 ? p2 : nullptr, m, si, G.prm.robust_kind, G.prm.robust_b, r, J1, J2);
+          double* o = sJ + lane * LDJ;
+          for (int t = 0; t < 36; t++) { o[t] = J1[t]; o[36 + t] = J2[t]; }
+          for (int t = 0; t < 6; t++) o[72 + t] = r[t];
         }
-      for (int a = 0; a < 6; a++) {
-        double b1 = 0, b2 = 0;
-        for (int k = 0; k < 6; k++) { b1 += J1[k * 6 + a] * r[k]; b2 += J2[k * 6 + a] * r[k]; }
-        o[108 + a] = b1; o[114 + a] = b2;
+        __syncthreads();
+        for (int q = tid; q < nf * 120; q += kThreads) {
+          const int fl = q / 120, en = q - fl * 120;
+          const double* J = sJ + fl * LDJ;
+          double acc = 0;
+          if (en < 108) {
+            const int blk = en / 36, ab = en - blk * 36, a = ab / 6, b = ab - a * 6;
+            const double* A = J + (blk == 1 ? 36 : 0);
+            const double* B = J + (blk == 0 ? 0 : 36);
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc += A[k * 6 + a] * B[k * 6 + b];
+          } else {
+            const int a = (en - 108) % 6;
+            const double* A = J + (en >= 114 ? 36 : 0);
+#pragma unroll
+            for (int k = 0; k < 6; k++) acc += A[k * 6 + a] * J[72 + k];
+          }
+          G.PF[(size_t)(f0 + fl) * 120 + en] = acc;
+        }
       }
+      __syncthreads();
     }
     for (int f = tid_team(); f < G.Elp; f += nthr_team()) {
       int l = G.lp_plane[f];
@@ -2314,9 +2336,19 @@ struct Phase {
       double* Wc = reinterpret_cast<double*>(sb + L.o_W);
       const double* Wg = G.W + (size_t)t0 * kWStride;
       for (int i = tid; i < nt * kWStride; i += kThreads) Wc[i] = ldc(Wg + i);
+      // the packed upper triangle of the symmetric block, folded into a 48 x 97 rectangle: row a < 48 keeps its entries (a, b) at
+      // [a][b]; row a >= 48 (96 - a entries) fills the unused left part of row 95 - a ([d] for d = b - a < 95 - a, the last one at
+      // [96]).  Same 4656 doubles, but every row is reached with a constant odd stride: the mat-vec below is a plain thread-per-row
+      // loop without bank conflicts, shuffles or index arithmetic.
       double* Bc = reinterpret_cast<double*>(sb + L.o_B);
       const double* Bg = G.Binv + (size_t)kb * kPackedBlock;
-      for (int i = tid; i < kPackedBlock; i += kThreads) Bc[i] = ldc(Bg + i);
+      for (int i = tid; i < kBlockDim * kBlockDim; i += kThreads) {
+        const int ra = i / kBlockDim, cb2 = i - ra * kBlockDim;
+        if (cb2 < ra) continue;
+        const double v = ldc(Bg + ra * kBlockDim - (ra * (ra - 1)) / 2 + (cb2 - ra));
+        const int fi = kBlockDim - 1 - ra, d = cb2 - ra;
+        Bc[ra < kBlockDim / 2 ? ra * 97 + cb2 : fi * 97 + (d < fi ? d : 96)] = v;
+      }
     }
     // ---- per-thread state: row `row` of pose p in owned block k ----
     const bool live = slot < nown;
@@ -2695,77 +2727,47 @@ struct Phase {
       }
       lap(14);
       {
-        // z = Binv r of every owned block, every element of the packed upper triangle read ONCE and conflict-free: up to five
-        // warps per block, a warp takes rows i = wi, wi + wps, ...; lanes are columns j = lane + 32 m.  Element (i, j), j > i,
-        // feeds z_i (b * r_j, summed across the lanes: eight rows per shuffle tree) and z_j (b * r_i, accumulated per lane, one
-        // partial per warp); the owner thread of a row adds the row sum and the warps' column partials in a fixed order.
-        const int wps = min(5, kWarps / max(nown, 1));   // (a CTA of a wide team may own no block at all)
-        const int ws = warp / wps, wi = warp - ws * wps;
-        if (ws < nown) {
-          unsigned char* sbs = g_smem + L.slot0 + ws * L.stride;
-          const double* cb = reinterpret_cast<const double*>(sbs + L.o_B);
-          const double* rv = sR + ws * kBlockDim;
-          double* zrow = reinterpret_cast<double*>(sbs);
-          const double rj0 = rv[lane], rj1 = rv[lane + 32], rj2 = rv[lane + 64];
-          double c0 = 0, c1 = 0, c2 = 0;
-          for (int ib = wi; ib < kBlockDim; ib += 8 * wps) {
-            // (branch-free: all loads of the batch are issued before the first use; rows past the end re-read row 95 with
-            // zero weights, columns left of the diagonal re-read earlier rows' entries and are masked)
-            double ra[8], bv[8][3], rr[8];
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-              const int i = min(ib + wps * t, kBlockDim - 1);
-              const double* rowp = cb + i * kBlockDim - (i * (i - 1)) / 2 - i;   // element (i, j) at rowp[j], j >= i
-              rr[t] = rv[i];
-              bv[t][0] = rowp[lane]; bv[t][1] = rowp[min(lane + 32, kBlockDim - 1)]; bv[t][2] = rowp[min(lane + 64, kBlockDim - 1)];
+        // z = Binv r of every owned block from the folded copy: four warps per block (rows 0-31, 32-47, 48-79, 80-95, so that
+        // a warp is on one side of the fold), a lane per row, two accumulators; consecutive lanes read consecutive or
+        // odd-strided words in every segment of the row.
+        double* sZ = sE;   // [96] per slot (scratch, free in phase C)
+        for (int task = warp; task < 4 * nown && G.prm.fine_timers != 3; task += kWarps) {   // (fine_timers == 3: timing experiment without the mat-vec)
+          const int s = task >> 2, part = task & 3;
+          const int uu = (part == 0 ? 0 : part == 1 ? 32 : part == 2 ? 48 : 80) + lane;
+          const bool act = (part & 1) ? lane < 16 : true;
+          unsigned char* sbs = g_smem + L.slot0 + s * L.stride;
+          const double* F = reinterpret_cast<const double*>(sbs + L.o_B);
+          const double* rv = sR + s * kBlockDim;
+          double a0 = 0, a1 = 0;
+          if (act) {
+            if (part < 2) {            // uu < 48: (j, uu) at [j][uu] for j < uu, (uu, j) at [uu][j] for j >= uu
+              const double* col = F + uu;
+              int j = 0;
+              for (; j + 1 < uu; j += 2) { a0 += col[j * 97] * rv[j]; a1 += col[(j + 1) * 97] * rv[j + 1]; }
+              if (j < uu) a0 += col[j * 97] * rv[j];
+              const double* rowp = F + uu * 97;
+              j = uu;
+              for (; j + 1 < kBlockDim; j += 2) { a0 += rowp[j] * rv[j]; a1 += rowp[j + 1] * rv[j + 1]; }
+              if (j < kBlockDim) a0 += rowp[j] * rv[j];
+            } else {                   // uu >= 48
+              const double* col = F + uu;
+#pragma unroll 4
+              for (int j = 0; j < 48; j += 2) { a0 += col[j * 97] * rv[j]; a1 += col[(j + 1) * 97] * rv[j + 1]; }
+              // 48 <= j < uu: (j, uu) lives in row 95 - j at [uu - j] (or [96] when uu == 95)
+              const int last = (uu == kBlockDim - 1) ? 1 : 0;
+              for (int j = 48; j < uu; j++) a0 += F[(kBlockDim - 1 - j) * 97 + (last ? 96 : uu - j)] * rv[j];
+              // j >= uu: (uu, j) lives in row fi = 95 - uu at [j - uu], the last one (j = 95) at [96]
+              const double* rowp = F + (kBlockDim - 1 - uu) * 97 - uu;
+              for (int j = uu; j < kBlockDim - 1; j++) a1 += rowp[j] * rv[j];
+              a1 += F[(kBlockDim - 1 - uu) * 97 + 96] * rv[kBlockDim - 1];
             }
-#pragma unroll
-            for (int t = 0; t < 8; t++) {
-              const int i = ib + wps * t;
-              const bool ok = i < kBlockDim;
-              const double b0 = (ok && lane >= i) ? bv[t][0] : 0.0, b1 = (ok && lane + 32 >= i) ? bv[t][1] : 0.0,
-                           b2 = (ok && lane + 64 >= i) ? bv[t][2] : 0.0;
-              ra[t] = b0 * rj0 + b1 * rj1 + b2 * rj2;
-              const double ri = rr[t];
-              c0 += (lane == i) ? 0.0 : b0 * ri;
-              c1 += (lane + 32 == i) ? 0.0 : b1 * ri;
-              c2 += (lane + 64 == i) ? 0.0 : b2 * ri;
-            }
-#pragma unroll
-            for (int t = 0; t < 4; t++) {
-              const bool hi = (lane & 16) != 0;
-              const double keep = hi ? ra[t + 4] : ra[t], send = hi ? ra[t] : ra[t + 4];
-              ra[t] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
-            }
-#pragma unroll
-            for (int t = 0; t < 2; t++) {
-              const bool hi = (lane & 8) != 0;
-              const double keep = hi ? ra[t + 2] : ra[t], send = hi ? ra[t] : ra[t + 2];
-              ra[t] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-            }
-            {
-              const bool hi = (lane & 4) != 0;
-              const double keep = hi ? ra[1] : ra[0], send = hi ? ra[0] : ra[1];
-              ra[0] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-            }
-            ra[0] += __shfl_xor_sync(0xffffffffu, ra[0], 2);
-            ra[0] += __shfl_xor_sync(0xffffffffu, ra[0], 1);
-            const int i = ib + wps * (((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1));
-            if ((lane & 3) == 0 && i < kBlockDim) zrow[i] = ra[0];
+            reinterpret_cast<double*>(sbs)[uu] = a0 + a1;
           }
-          double* colp = zrow + kBlockDim + wi * kBlockDim;
-          colp[lane] = c0; colp[lane + 32] = c1; colp[lane + 64] = c2;
         }
         lap1(22);
         __syncthreads();
         lap1(23);
-        if (on) {
-          const double* zr = sE;
-          double zl = zr[u];
-          for (int w = 0; w < wps; w++) zl += zr[kBlockDim + w * kBlockDim + u];
-          z_u = zl;
-          dot += r_u * zl;
-        }
+        if (on) { z_u = sZ[u]; dot += r_u * z_u; }
       }
       lap(15);
       const double rz_new = team_reduce_flag(c, dot);
