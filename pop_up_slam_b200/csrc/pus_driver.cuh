@@ -134,7 +134,8 @@ __device__ void run_graph_impl(Ctx& c) {
   const LmParams& P = G.prm;
   const bool lead = (c.rank == 0 && threadIdx.x == 0);
   LmResult* res = G.res;
-  Timer tm(lead);
+  const bool tlead = (c.rank == (P.timer_rank < c.tsize ? P.timer_rank : 0) && threadIdx.x == 0);
+  Timer tm(tlead);
   Timer& ft = tm;
   ph.ft = (P.fine_timers ? &tm : nullptr);
   if (lead) {
@@ -164,7 +165,7 @@ __device__ void run_graph_impl(Ctx& c) {
       double v[1] = {1.0};
       for (int i = 0; i < 1000; i++) { v[0] = 1.0; team_reduce<1>(c, G.red, v); }
       tm.lap(1);
-      if (lead) tm.flush(res);
+      if (tlead) tm.flush(res);
       return;
     }
     if (P.debug_stage == 3) {  // q = S * pv[0] with the current linearisation / Schur set-up
@@ -186,7 +187,7 @@ __device__ void run_graph_impl(Ctx& c) {
         if (lead) { res->pcg_iters = its; res->chi2_final = dn; }
       }
     }
-    if (lead) tm.flush(res);
+    if (tlead) tm.flush(res);
     return;
   }
 
@@ -306,6 +307,8 @@ __device__ void run_graph_impl(Ctx& c) {
     res->pcg_iters = pcg_total; res->chi2_initial = err0; res->chi2_final = err;
     res->trace_n = iter < kTraceCap ? iter : kTraceCap;
     res->status = prec_builds;
+  }
+  if (tlead) {
     tm.acc[5] = (unsigned long long)prec_builds * 1000000ull;
     tm.flush(res);
   }

@@ -335,6 +335,7 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
   p.refresh_pct = s->opt.reserved[3] > 0 ? s->opt.reserved[3] : (s->c.levels == 3 ? 200 : 130);
   p.refresh_add = 8;
   p.fine_timers = (s->opt.reserved[2] & 128) ? 3 : (s->opt.reserved[2] & 64) ? 2 : ((s->opt.reserved[2] & 1) ? 1 : 0);   // bit 6: sub-phases of linearize instead     // reserved[2] bit 0: sub-phase timers inside the PCG phases
+  p.timer_rank = (s->opt.reserved[2] >> 8) & 0xff;   // bits 8-15: the CTA that keeps the phase timers
   p.tma_mode = (s->opt.reserved[2] & 2) ? 1 : ((s->opt.reserved[2] & 4) ? 2 : 0);  // bit 1: always stage tiles by TMA, bit 2: never
   p.warm_start = s->opt.reserved[1] == 1 ? 0 : 1;      // reserved[1] = 1: never warm-start PCG after a rejected step  // reserved[0] = 1: rebuild the preconditioner every solve
   p.mode = mode; p.debug_stage = debug_stage; p.debug_lambda = debug_lambda; p.restore_init = restore_init;
@@ -345,6 +346,9 @@ static int auto_team(const Solver* s, int limit) {
   int need = std::max((s->c.ntile + kWarps - 1) / kWarps, (s->c.nblk + kSlots - 1) / kSlots);
   need = std::max(need, (6 * s->c.nc + kWarps - 1) / kWarps);  // one warp per row of the coarse inverse
   need = std::max(need, (6 * s->c.nc_pad + 15) / 16);           // <= two 8-row MMA tiles per CTA in the coarse inversion
+  // a CTA per 16-pose block when the device has room: the phases of the PCG loop are latency-bound, so fewer owned blocks per
+  // CTA shorten every phase (config 2, 19 blocks: 3.04 ms on 19 CTAs against 3.32 ms on 9)
+  if (s->c.nblk <= limit) return std::min(std::max(std::max(need, s->c.nblk), 1), limit);
   if (need * 2 > limit) need = limit;   // a graph that wants most of the device gets all of it (config 3: 148 CTAs are 1.2 % faster than 120)
   return std::min(std::max(need, 1), limit);
 }

@@ -48,6 +48,7 @@ struct LmParams {
   int tma_mode;      // 0: TMA-staged W/Wt tiles when a warp owns several tiles (large graphs), 1: always, 2: never
   int blocks_always; // 1: the dense 16-pose blocks (level 1) are rebuilt for every linear solve, only the coarse level(s) lazily
   int jac_numeric;   // 1: reference-Jacobian mode (central differences, numericalDiff.cpp:41-87) instead of the closed forms
+  int timer_rank;    // CTA of the team whose thread 0 keeps the phase timers (diagnostics; default 0)
   int resident;      // 1: the PCG loop runs block-resident (pcg_resident: operator, preconditioner blocks and vectors of the owned
                      //    pose blocks stay in shared memory / registers; set by the host when the layout fits the team)
 };
@@ -458,6 +459,40 @@ __device__ __forceinline__ double team_reduce_flag(Ctx& c, double v) {
   if (lane == 0) s[warp * 4] = v;
   __syncthreads();
   c.red_seq++;
+  const int nw = (c.tsize + 31) >> 5;
+  if (c.tsize > 1 && nw <= kWarps) {
+    // one slot per thread: warp w polls slots 32 w .. 32 w + 31 (a single round trip to L2 for the whole team instead of
+    // tsize / 32 dependent ones by warp 0), butterfly sum per warp, then every thread adds the nw warp sums in warp order
+    const unsigned seq = c.red_seq;
+    unsigned long long* slots = c.rflag + (size_t)(seq & 1u) * c.tsize * 2;
+    if (warp == 0) {
+      double acc = (lane < kWarps) ? s[lane * 4] : 0.0;
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        const unsigned long long b = (unsigned long long)__double_as_longlong(acc);
+        st_relaxed_u64(slots + (size_t)c.rank * 2, (b & 0xffffffffull) | ((unsigned long long)seq << 32));
+        st_release_u64(slots + (size_t)c.rank * 2 + 1, (b >> 32) | ((unsigned long long)seq << 32));   // (orders every prior write)
+      }
+    }
+    if (warp < nw) {
+      const int r = warp * 32 + lane;
+      double val = 0;
+      if (r < c.tsize) {
+        unsigned long long w0, w1;
+        do {
+          w0 = ld_relaxed_u64(slots + (size_t)r * 2);
+          w1 = ld_relaxed_u64(slots + (size_t)r * 2 + 1);
+        } while ((unsigned)(w0 >> 32) != seq || (unsigned)(w1 >> 32) != seq);
+        val = __longlong_as_double((long long)((w0 & 0xffffffffull) | (w1 << 32)));
+      }
+      val = warp_sum(val);
+      if (lane == 0) s[warp * 4 + 1] = val;
+    }
+    __syncthreads();
+    double tot = 0;
+    for (int w = 0; w < nw; w++) tot += s[w * 4 + 1];
+    return tot;
+  }
   if (warp == 0) {
     double acc = (lane < kWarps) ? s[lane * 4] : 0.0;
     acc = warp_sum(acc);
