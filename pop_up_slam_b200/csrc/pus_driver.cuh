@@ -325,7 +325,7 @@ __device__ void run_graph(Ctx& c) {
   }
 }
 
-__global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs, int n_graphs, int team_ctas, unsigned* bars) {
+__global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs, int n_graphs, int team_ctas, unsigned* bars, int cluster) {
   unsigned char* const smem = g_smem;
   const int n_teams = gridDim.x / team_ctas;
   const int team = blockIdx.x / team_ctas;
@@ -345,7 +345,10 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
   c.rflag = reinterpret_cast<unsigned long long*>(bars + 8192) + (size_t)team * team_ctas * 4;
   c.red_seq = 0;
   c.light = 0;
+  c.cluster = (cluster && team_ctas > 1) ? 1 : 0;   // launched with cluster dimension = team_ctas
+  c.cl_par = 0;
   if (threadIdx.x == 0) {
+    if (c.cluster) mbar_init(reinterpret_cast<unsigned long long*>(smem + kSmClBar), (unsigned)team_ctas);
     unsigned long long* gbar = reinterpret_cast<unsigned long long*>(smem + kSmGjBar);
     mbar_init(gbar, 1);
     mbar_init(gbar + 1, 1);
@@ -358,6 +361,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
     fence_mbar_init();
   }
   __syncthreads();
+  if (c.cluster) cluster_sync_all();   // every CTA of the cluster runs before the first store into a peer's shared memory
   for (int g = team; g < n_graphs; g += n_teams) {
     __syncthreads();
     const int* src = reinterpret_cast<const int*>(graphs + g);
@@ -366,6 +370,7 @@ __global__ void __launch_bounds__(kThreads, 1) lm_kernel(const DevGraph* graphs,
     __syncthreads();
     run_graph(c);
   }
+  if (c.cluster) cluster_sync_all();   // no CTA exits while a peer may still address its shared memory
 }
 
 

@@ -146,6 +146,8 @@ struct Ctx {
   unsigned long long* rflag;   // flag-stamped reduction slots of this team ([2 sets][tsize][2 words], zeroed by the host per launch)
   unsigned red_seq;      // sequence number of the last flag-stamped reduction (same on every thread of the team)
   int light;             // 1: team_barrier() / team_reduce<1>() use the fence-free barrier and the flag-stamped reduction
+  int cluster;           // 1: the team is one thread-block cluster (small graphs): cluster barrier / DSMEM mbarrier, reductions through DSMEM
+  unsigned cl_par;       // phase parity of the cluster mbarrier (same on every thread)
 };
 
 __device__ __forceinline__ double ldc(const double* p) { return __ldcg(p); }
@@ -179,7 +181,50 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   return v;
 }
+// Teams of up to 16 CTAs are launched as one thread-block cluster.  Outside the PCG loops the team barrier is the hardware
+// cluster barrier (every thread arrives; release / acquire at cluster scope = the fences + L1 invalidation of the
+// global-counter barrier).  Inside the loops (`light`) it is an mbarrier in every CTA's shared memory that counts one remote
+// arrival per CTA of the cluster: a lane per peer sends `mbarrier.arrive.release.cluster` through DSMEM (one warp-wide fence
+// orders the CTA's global writes, through the CTA barrier, before the arrivals), thread 0 polls its own mbarrier with a
+// relaxed wait -- no L1 invalidation (the spilled loop state stays cached), and everything another CTA wrote is read with
+// ld.global.cg as in the global-counter version.  One-value reductions ride on the same arrival: the partial is stored into
+// slot [rank] of every peer's buffer before the arrive.
+constexpr int kSmClBar = 1056;   // the cluster mbarrier (u64), between the pipeline mbarriers and the work area
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ unsigned mapa_u32(unsigned a, unsigned cta) {
+  unsigned ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(a), "r"(cta));
+  return ra;
+}
+__device__ __forceinline__ void st_dsmem_f64(const void* local_smem, unsigned cta, double v) {
+  asm volatile("st.shared::cluster.f64 [%0], %1;" ::"r"(mapa_u32((unsigned)__cvta_generic_to_shared(local_smem), cta)), "d"(v) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_peer_release(unsigned local_bar, unsigned cta) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(mapa_u32(local_bar, cta)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned bar, unsigned parity) {
+  unsigned ok;
+  do {
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.relaxed.cluster.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(ok)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  } while (!ok);
+}
+__device__ __forceinline__ void cluster_barrier_light(Ctx& c) {
+  __syncthreads();
+  if (threadIdx.x < 32) {
+    const unsigned b = (unsigned)__cvta_generic_to_shared(g_smem + kSmClBar);
+    if ((int)threadIdx.x < c.tsize) mbar_arrive_peer_release(b, threadIdx.x);
+    if (threadIdx.x == 0) mbar_wait_relaxed(b, c.cl_par);
+  }
+  c.cl_par ^= 1u;
+  __syncthreads();
+}
 __device__ __forceinline__ void team_barrier_light(Ctx& c) {
+  if (c.cluster) { cluster_barrier_light(c); return; }
   __syncthreads();
   if (c.tsize > 1) {
     if (threadIdx.x == 0) {
@@ -196,6 +241,7 @@ __device__ __forceinline__ void team_barrier_light(Ctx& c) {
 // atomics through peer-mapped memory), and waits for its own counter.
 __device__ __forceinline__ void team_barrier(Ctx& c) {
   if (c.light) { team_barrier_light(c); return; }   // inside the single-GPU PCG loops (set / cleared by schur_solve)
+  if (c.cluster) { cluster_sync_all(); return; }
   __syncthreads();
 #ifndef PUS_NO_SPAN
   if (c.mirror) {
@@ -459,6 +505,26 @@ __device__ __forceinline__ double team_reduce_flag(Ctx& c, double v) {
   if (lane == 0) s[warp * 4] = v;
   __syncthreads();
   c.red_seq++;
+  if (c.cluster) {
+    // every CTA leaves its partial in slot [rank] of every CTA's buffer (two buffers, by the parity of the sequence number: a
+    // CTA can be one reduction ahead of the slowest reader) and then arrives on that CTA's mbarrier; fixed-order sum
+    const int b = 2 + (int)(c.red_seq & 1u);
+    if (warp == 0) {
+      double acc = (lane < kWarps) ? s[lane * 4] : 0.0;
+      acc = warp_sum(acc);
+      const unsigned mb = (unsigned)__cvta_generic_to_shared(g_smem + kSmClBar);
+      if (lane < c.tsize) {
+        st_dsmem_f64(s + c.rank * 4 + b, (unsigned)lane, acc);
+        mbar_arrive_peer_release(mb, (unsigned)lane);
+      }
+      if (lane == 0) mbar_wait_relaxed(mb, c.cl_par);
+    }
+    c.cl_par ^= 1u;
+    __syncthreads();
+    double tot = 0;
+    for (int r = 0; r < c.tsize; r++) tot += s[r * 4 + b];
+    return tot;
+  }
   const int nw = (c.tsize + 31) >> 5;
   if (c.tsize > 1 && nw <= kWarps) {
     // one slot per thread: warp w polls slots 32 w .. 32 w + 31 (a single round trip to L2 for the whole team instead of
