@@ -388,7 +388,9 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
   int use_cluster = 0;
   {
     static const int max_cluster = [] { const char* e = getenv("PUS_CLUSTER"); int v = e ? atoi(e) : 16; return v < 0 ? 0 : (v > 16 ? 16 : v); }();
-    if (!spanning && max_cluster > 1 && team > 1) {
+    bool off = false;
+    for (int i = 0; i < n; i++) off = off || (ss[i]->opt.reserved[2] & (1 << 16));   // reserved[2] bit 16: global-memory barrier only
+    if (!spanning && !off && max_cluster > 1 && team > 1) {
       int cl = 2;
       while (cl * 2 <= std::min(team, max_cluster)) cl *= 2;
       int t = 0;

@@ -424,6 +424,40 @@ def test_resident_solve_is_repeatable():
     assert np.array_equal(P, b.get_poses(idb["pose_ids"]))   # fixed-order reductions: bit-reproducible
 
 
+def _solve_with_flags(g, flags, team=0):
+    import ctypes
+    a = GpuGraphAPI()
+    ids = gg.build_bulk(a, g)
+    gg.configure(a, g)
+    o = a.get_solver_options()
+    o.reserved[2] = flags
+    o.team_ctas = team
+    a._chk(a.lib.pus_set_solver_options(a.h, ctypes.byref(o)))
+    it = a.batch_optimize()
+    return it, a.chi2(), a.get_poses(ids["pose_ids"]), a.get_planes(ids["plane_ids"]), a.stats(), a.trace()
+
+
+@pytest.mark.parametrize("team", [0, 2, 4, 8])
+def test_cluster_teams_match_global_barrier_teams(team):
+    """Small teams run as one thread-block cluster (cluster barrier, DSMEM mbarrier and reductions); solver option reserved[2]
+    bit 16 keeps the global-memory barrier.  Same LM trace and the same answer either way, and as the oracle."""
+    g = gg.make_config(2, seed=11)
+    it_c, chi_c, P_c, L_c, st_c, tr_c = _solve_with_flags(g, 0, team)
+    it_g, chi_g, P_g, L_g, st_g, tr_g = _solve_with_flags(g, 1 << 16, team)
+    assert it_c == it_g
+    assert tr_c["accepted"].tolist() == tr_g["accepted"].tolist()
+    assert abs(chi_c - chi_g) <= 1e-9 * abs(chi_g)
+    assert np.abs(P_c - P_g).max() < 1e-8 and np.abs(L_c - L_g).max() < 1e-8
+    if team == 0:
+        assert st_c["grid_ctas"] == 16 and st_g["grid_ctas"] == 19   # one 16-CTA cluster / a CTA per pose block
+    orc = OracleAPI()
+    io = gg.build_bulk(orc, g)
+    gg.configure(orc, g)
+    assert orc.batch_optimize() == it_c
+    assert abs(chi_c - orc.chi2()) <= 1e-6 * abs(chi_c)
+    assert np.abs(P_c[:, :3] - orc.get_poses(io["pose_ids"])[:, :3]).max() < 1e-5
+
+
 def test_popup_fit_matches_oracle():
     rng = np.random.default_rng(7)
     nf = 50
