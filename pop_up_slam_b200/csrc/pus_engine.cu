@@ -341,6 +341,14 @@ static void fill_params(Solver* s, LmParams& p, int mode, int restore_init, int 
   p.mode = mode; p.debug_stage = debug_stage; p.debug_lambda = debug_lambda; p.restore_init = restore_init;
 }
 
+// block-resident PCG loop: two levels with one hat node per pose block, every CTA's owned blocks in one round, and the per-CTA
+// layout (W tiles + packed preconditioner block + records per owned block) within the shared memory of an SM
+static bool resident_fits(const Compiled& cc, int team) {
+  const int nown = (cc.nblk + team - 1) / team;
+  return cc.levels == 2 && cc.SP == kBlockPoses && nown >= 1 && nown <= kSlots && cc.res_ng <= 511 && cc.res_np <= 8191 &&
+         res_layout(cc.res_nt, cc.res_ng, cc.res_np, 6 * cc.nc, nown).total <= (size_t)kSmemBytes;
+}
+
 static int auto_team(const Solver* s, int limit) {
   if (s->opt.team_ctas > 0) return std::min(std::max(1, s->opt.team_ctas), limit);
   int need = std::max((s->c.ntile + kWarps - 1) / kWarps, (s->c.nblk + kSlots - 1) / kSlots);
@@ -374,6 +382,35 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
     int need = 1;
     for (int i = 0; i < n; i++) need = std::max(need, auto_team(ss[i], max_ctas));
     team = std::min(share, need);
+    // Several waves of larger teams can beat one wave of small ones: the block-resident PCG loop only fits when a CTA owns few
+    // pose blocks, and the general loop is 2-3 times slower per solve.  Cost model fitted on TUM-scale graphs (19 blocks; ms per
+    // solve: resident 3.2 / 3.6 at 2 / 3 blocks per CTA; general 8.3 at 5, 13.0 at 7, 12.4 at 10 blocks per CTA, i.e. by the
+    // number of rounds over kSlots blocks), used as a ratio only:
+    // cost(t) = waves(t) * (resident ? 3.0 + 0.2 b : 4.3 + 4.2 ceil(b / kSlots)), b = blocks per CTA.  32 graphs on one GPU: two
+    // waves of sixteen 9-CTA teams (7.7 ms) instead of 4-CTA teams (8.3 ms); 64 graphs keep 2-CTA teams (11.4 ms against four
+    // waves = 14.4 ms).
+    bool forced = false;
+    for (int i = 0; i < n; i++) forced = forced || ss[i]->opt.team_ctas > 0 || ss[i]->hd.span_w > 1;
+    if (!forced) {
+      double best = 1e300;
+      int best_t = team;
+      for (int t = 1; t <= std::min(need, max_ctas); t++) {
+        const int teams_t = std::min(n, max_ctas / t), waves = (n + teams_t - 1) / teams_t;
+        double worst = 0;
+        bool ok = true;
+        for (int i = 0; i < n && ok; i++) {
+          const Compiled& cc = ss[i]->c;
+          if (kSmWork + gj_smem_bytes(6 * cc.nc_pad, t) > (size_t)kSmemBytes) { ok = false; break; }
+          const int b = (cc.nblk + t - 1) / t;
+          const bool res = resident_fits(cc, t) && !(ss[i]->opt.reserved[2] & 32);
+          worst = std::max(worst, res ? 3.0 + 0.2 * b : 4.3 + 4.2 * ((b + kSlots - 1) / kSlots));
+        }
+        if (!ok) continue;
+        const double cost = waves * worst;
+        if (cost <= best) { best = cost; best_t = t; }   // (ties: the larger team)
+      }
+      team = best_t;
+    }
     int teams = std::min(n, max_ctas / team);
     grid = teams * team;
   }
@@ -431,10 +468,7 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
     {
       // block-resident PCG loop: two levels with one hat node per pose block, every CTA's owned blocks in one round, and the
       // per-CTA layout (W tiles + packed preconditioner block + records per owned block) within the shared memory of an SM
-      const Compiled& cc = ss[i]->c;
-      const int nown = (cc.nblk + team - 1) / team;
-      const bool fits = cc.levels == 2 && cc.SP == kBlockPoses && nown >= 1 && nown <= kSlots && cc.res_ng <= 511 && cc.res_np <= 8191 &&
-                        res_layout(cc.res_nt, cc.res_ng, cc.res_np, 6 * cc.nc, nown).total <= kSmemBytes;
+      const bool fits = resident_fits(ss[i]->c, team);
       ss[i]->hd.prm.resident = (fits && !(ss[i]->opt.reserved[2] & 32) && ss[i]->hd.span_w <= 1) ? 1 : 0;   // reserved[2] bit 5: off
     }
     hg[i] = ss[i]->hd;
