@@ -71,6 +71,7 @@ struct Solver {
   int borrow_depth = 0;
   bool values_dirty = false;             // host values changed since the last upload (pus_init_*): device copies are stale
   DevGraph* d_batch = nullptr;           // parameter blocks of a batched launch (grow-only)
+  LmResult* d_batch_res = nullptr;       // results of a batched launch, contiguous: ONE device->host copy per batch
   int d_batch_cap = 0;
   // resident tables of pus_refresh_bind / pus_refresh_run (frames' ground segments, invK, factor <-> plane-row map)
   struct RefreshTables {
@@ -444,8 +445,14 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = t; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        int active = 0;
-        if (cudaOccupancyMaxActiveClusters(&active, (void*)kplain::lm_kernel, &cfg) == cudaSuccess && active >= teams) {
+        static int active_cache[17] = {-1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1, -1};   // per cluster size (one device type per process)
+        int active = active_cache[t];
+        if (active < 0) {
+          active = 0;
+          if (cudaOccupancyMaxActiveClusters(&active, (void*)kplain::lm_kernel, &cfg) != cudaSuccess) { active = 0; cudaGetLastError(); }
+          active_cache[t] = active;
+        }
+        if (active >= teams) {
           team = t; grid = teams * t; use_cluster = 1;
         } else {
           cudaGetLastError();
@@ -477,11 +484,14 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
   if (n > 1) {
     if (s0->d_batch_cap < n) {
       if (s0->d_batch) cudaFree(s0->d_batch);
-      s0->d_batch = nullptr; s0->d_batch_cap = 0;
+      if (s0->d_batch_res) cudaFree(s0->d_batch_res);
+      s0->d_batch = nullptr; s0->d_batch_res = nullptr; s0->d_batch_cap = 0;
       CUDA_OK(cudaMalloc(&s0->d_batch, sizeof(DevGraph) * (size_t)n));
+      CUDA_OK(cudaMalloc(&s0->d_batch_res, sizeof(LmResult) * (size_t)n));
       s0->d_batch_cap = n;
     }
     d_graphs = s0->d_batch;
+    for (int i = 0; i < n; i++) hg[i].res = s0->d_batch_res + i;   // (the handles' own result slots are not used by this launch)
   }
   CUDA_OK(cudaMemcpyAsync(d_graphs, hg.data(), sizeof(DevGraph) * n, cudaMemcpyHostToDevice, s0->stream));
   CUDA_OK(cudaMemsetAsync(s0->d_bar, 0, 32 * 1024 * sizeof(unsigned), s0->stream));
@@ -511,10 +521,20 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
   if (se != cudaSuccess) { g_err = std::string("lm_kernel: ") + cudaGetErrorString(se); return -1; }
   float ms = 0;
   CUDA_OK(cudaEventElapsedTime(&ms, s0->ev0, s0->ev1));
+  std::vector<LmResult> hres;
+  if (n > 1) {
+    hres.resize(n);
+    CUDA_OK(cudaMemcpyAsync(hres.data(), s0->d_batch_res, sizeof(LmResult) * (size_t)n, cudaMemcpyDeviceToHost, s0->stream));
+    CUDA_OK(cudaStreamSynchronize(s0->stream));
+  }
   for (int i = 0; i < n; i++) {
     Solver* s = ss[i];
-    CUDA_OK(cudaMemcpyAsync(&s->res, s->d_res, sizeof(LmResult), cudaMemcpyDeviceToHost, s0->stream));
-    CUDA_OK(cudaStreamSynchronize(s0->stream));
+    if (n > 1) {
+      s->res = hres[i];
+    } else {
+      CUDA_OK(cudaMemcpyAsync(&s->res, s->d_res, sizeof(LmResult), cudaMemcpyDeviceToHost, s0->stream));
+      CUDA_OK(cudaStreamSynchronize(s0->stream));
+    }
     pus_stats& st = s->stats;
     st.lm_iterations = s->res.iterations; st.accepted = s->res.accepted; st.relinearizations = s->res.relin;
     st.chi2_evals = s->res.chi2_evals; st.pcg_iterations = s->res.pcg_iters; st.chi2_initial = s->res.chi2_initial;
@@ -641,6 +661,7 @@ int pus_destroy(pus_handle h) {
   for (void* pp : s->span_peers) if (pp) cudaIpcCloseMemHandle(pp);
   s->free_device();
   if (s->d_batch) cudaFree(s->d_batch);
+  if (s->d_batch_res) cudaFree(s->d_batch_res);
   if (s->rt.mem) cudaFree(s->rt.mem);
   if (s->scratch) cudaFree(s->scratch);
   if (s->ev0) cudaEventDestroy(s->ev0);
