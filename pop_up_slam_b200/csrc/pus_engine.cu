@@ -512,6 +512,11 @@ static int launch(Solver** ss, int n, int mode, int restore_init, int debug_stag
     at[0].val.clusterDim.x = team; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
     le = cudaLaunchKernelExC(&cfg, kfn, args);
+    if (le != cudaSuccess) {   // (never seen; the same grid also runs with the global-memory barrier)
+      cudaGetLastError();
+      use_cluster = 0; a4 = 0;
+      le = cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kThreads), args, kSmemBytes, s0->stream);
+    }
   } else {
     le = cudaLaunchCooperativeKernel(kfn, dim3(grid), dim3(kThreads), args, kSmemBytes, s0->stream);
   }
