@@ -241,6 +241,16 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
 
   // ---- split factors ----
   std::vector<int> ppf;  // pose-plane factor ids in insertion order
+  {
+    int npp = 0, npf = 0, nlp = 0;
+    for (const HFactor& F : g.factors) {
+      if (!F.alive) continue;
+      if (F.kind == F_POSE_PLANE) npp++; else if (F.kind == F_PLANE_PRIOR) nlp++; else npf++;
+    }
+    ppf.reserve(npp);
+    c.pf_fid.reserve(npf); c.pf_i.reserve(npf); c.pf_j.reserve(npf); c.pf_meas.reserve((size_t)npf * 6); c.pf_sinf.reserve((size_t)npf * 21);
+    c.lp_fid.reserve(nlp); c.lp_plane.reserve(nlp); c.lp_meas.reserve((size_t)nlp * 4); c.lp_sinf.reserve((size_t)nlp * 6);
+  }
   for (int f = 0; f < (int)g.factors.size(); f++) {
     const HFactor& F = g.factors[f];
     if (!F.alive) continue;
@@ -281,7 +291,7 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   {
     // count edges per pose, then lay the slots out block by block
     std::vector<int> cnt(N, 0);
-    for (int i = 0; i < E; i++) cnt[c.node_idx[g.factors[ppf[order[i]]].nodes[0]]]++;
+    for (int i = 0; i < E; i++) cnt[key[i]]++;   // (the keys gathered for the counting sort)
     int slot = 0;
     for (int k = 0; k < c.nblk; k++) {
       c.tile_ptr[k] = slot / kTile;
@@ -303,7 +313,7 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
     std::vector<int> fill(c.pp_ptr.begin(), c.pp_ptr.begin() + N);
     for (int i = 0; i < E; i++) {
       const HFactor& F = g.factors[ppf[order[i]]];
-      int p = c.node_idx[F.nodes[0]];
+      int p = key[order[i]];
       int e = fill[p]++;
       c.pp_fid[e] = ppf[order[i]];
       c.pp_pose[e] = p;
@@ -434,11 +444,17 @@ inline bool compile_graph(const Graph& g, Compiled& c, std::string& err) {
   c.blk_simple.assign(c.nblk, 0);
   c.grp_of_slot.assign(slots, 0);
   c.grp_mem_ptr.clear(); c.grp_mem.clear(); c.grp_plane.clear();
+  c.grp_mem.reserve(E); c.grp_plane.reserve(E / 2 + 16); c.grp_mem_ptr.reserve(E / 2 + 16);
+  std::vector<unsigned long long> ekey;
+  std::vector<int> es;
   for (int k = 0; k < c.nblk; k++) {
     int e0 = c.tile_ptr[k] * kTile, e1 = c.tile_ptr[k + 1] * kTile;
-    std::vector<int> es;
-    for (int e = e0; e < e1; e++) if (c.pp_pose[e] >= 0) es.push_back(e);
-    std::stable_sort(es.begin(), es.end(), [&](int a, int b) { return c.pp_plane[a] < c.pp_plane[b]; });
+    // (plane, slot) packed into one integer: an integer sort gives the order of a stable sort by plane over the slot order
+    ekey.clear();
+    for (int e = e0; e < e1; e++) if (c.pp_pose[e] >= 0) ekey.push_back(((unsigned long long)(unsigned)c.pp_plane[e] << 32) | (unsigned)e);
+    std::sort(ekey.begin(), ekey.end());
+    es.resize(ekey.size());
+    for (size_t i = 0; i < ekey.size(); i++) es[i] = (int)(unsigned)(ekey[i] & 0xffffffffull);
     int g0 = (int)c.grp_plane.size();
     for (int i = 0; i < (int)es.size(); i++) {
       if (i == 0 || c.pp_plane[es[i]] != c.pp_plane[es[i - 1]]) {

@@ -3,7 +3,7 @@
 // Use it to prove that a host-side refactor leaves the image bit-identical:
 //   g++ -O2 -std=c++17 -DHDR='"<old checkout>/pop_up_slam_b200/csrc/pus_graph.hpp"' -x c++ tools/compile_graph_hash.cpp -o /tmp/h_old
 //   g++ -O2 -std=c++17 -DHDR='"pop_up_slam_b200/csrc/pus_graph.hpp"'               -x c++ tools/compile_graph_hash.cpp -o /tmp/h_new
-//   for a in "40 6 1" "300 8 2" "2000 12 3" "20000 20 5"; do /tmp/h_old $a; /tmp/h_new $a; done      (args: poses, edges/pose, seed)
+//   for a in "40 6 1" "300 8 2" "2000 12 3" "20000 20 5"; do /tmp/h_old $a; /tmp/h_new $a; done      (args: poses, edges/pose, seed [, force_levels])
 #include <chrono>
 #include <cstdio>
 #include <cstdint>
@@ -38,11 +38,14 @@ int main(int argc, char** argv) {
     }
   }
   if (!planes.empty()) { double m4[4] = {0, 0, 1, 0}; g.add_plane_prior(planes[0], m4, s6); }
+  if (argc > 4) g.force_levels = atoi(argv[4]);
   Compiled c; std::string err;
   auto t0 = std::chrono::steady_clock::now();
   bool ok = compile_graph(g, c, err);
   double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+  auto t1 = std::chrono::steady_clock::now();
   ok = compile_graph(g, c, err) && ok;   // a second compile into the same object must give the same image
+  const double ms2 = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t1).count();
   for (int x : {c.N, c.M, c.Epl, c.Epf, c.Elp, c.SP, c.nc_pad, c.ntile, c.nslot, c.nblk, c.nc, c.n_upart, c.n_ypart, c.nce, c.ngrp, c.n_hv, c.n_heavy, c.n_huge, c.n_f2, c.ntile_pl}) hi(x);
   hv(c.pose_node); hv(c.plane_node); hv(c.node_idx); hv(c.pose_val); hv(c.plane_val);
   hv(c.pp_fid); hv(c.pp_pose); hv(c.pp_plane); hv(c.pp_ptr); hv(c.pm2pl); hv(c.pm_part); hv(c.ypart_ptr); hv(c.tile_ptr); hv(c.blk_part_ptr); hv(c.grp_of_slot);
@@ -53,5 +56,9 @@ int main(int argc, char** argv) {
   hv(c.blk_grp_ptr); hv(c.grp_plane); hv(c.grp_mem_ptr); hv(c.grp_mem); hv(c.blk_simple); hv(c.grp_info);
   hv(c.ce_ptr); hv(c.ce_node); hv(c.ce_plane); hv(c.ce_lo); hv(c.ce_hi); hv(c.n2ce_ptr); hv(c.n2ce);
   hv(c.hv_plane); hv(c.lp_ptr); hv(c.lp_cea); hv(c.lp_ceb); hv(c.fp_ptr); hv(c.fp_f);
-  printf("N=%d per=%d seed=%d ok=%d E=%d hash=%016llx  (%.2f ms) %s\n", N, per, seed, ok, c.Epl, (unsigned long long)H, ms, err.c_str());
+  // (members added in round 2: resident-loop records, assembly tasks, the level-2 pairs of the three-level preconditioner)
+  for (int x : {c.res_nt, c.res_ng, c.res_np, c.n_atask, c.n_asplit, c.levels, c.nc2, c.nce2, c.ng2}) hi(x);
+  hv(c.grp_info2); hv(c.at_plane); hv(c.at_lo); hv(c.at_hi); hv(c.at_ptr); hv(c.as_plane);
+  hv(c.ce2_ptr); hv(c.ce2_node); hv(c.ce2_plane); hv(c.ce2_lo); hv(c.ce2_hi); hv(c.g2_ptr); hv(c.g2_ce);
+  printf("N=%d per=%d seed=%d ok=%d E=%d hash=%016llx  (%.2f ms, again %.2f ms) %s\n", N, per, seed, ok, c.Epl, (unsigned long long)H, ms, ms2, err.c_str());
 }
